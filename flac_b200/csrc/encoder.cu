@@ -1,0 +1,506 @@
+// encoder.cu -- host side of the B200 FLAC block encoder + its C ABI (include/flac_b200.h).
+//
+// The host does what the reference does once per (encoder, blocksize): validate settings
+// (init_stream_internal_, src/libFLAC/stream_encoder.c:725-830), generate the apodization
+// tables with the HOST libm's cosf exactly as src/libFLAC/window.c:195-220 does (CUDA's
+// cosf is not bit-identical to glibc's: SURVEY.md §0.4) and expand the apodization
+// state machine (apply_apodization_, :4318-4392) into a static list of autocorrelation
+// sections and LPC candidates. Everything per block runs in the kernels.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "encode_kernels.cuh"
+
+namespace fb200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+// src/libFLAC/window.c:46-55, 136-143, 195-220 (FLAC__window_rectangle / _hann / _tukey)
+static void window_tukey(float *window, int32_t L, float p)
+{
+	if(p <= 0.0) {
+		for(int32_t n = 0; n < L; n++) window[n] = 1.0f;
+	}
+	else if(p >= 1.0) {
+		const int32_t N = L - 1;
+		for(int32_t n = 0; n < L; n++) window[n] = (float)(0.5f - 0.5f * cosf(2.0f * M_PI * n / N));
+	}
+	else if(!(p > 0.0f && p < 1.0f)) {
+		window_tukey(window, L, 0.5f);
+	}
+	else {
+		const int32_t Np = (int32_t)(p / 2.0f * L) - 1;
+		for(int32_t n = 0; n < L; n++) window[n] = 1.0f;
+		if(Np > 0) {
+			for(int32_t n = 0; n <= Np; n++) {
+				window[n] = (float)(0.5f - 0.5f * cosf(M_PI * n / Np));
+				window[L - Np - 1 + n] = (float)(0.5f - 0.5f * cosf(M_PI * (n + Np) / Np));
+			}
+		}
+	}
+}
+
+struct Geometry {
+	int bs = 0;
+	EncK k{};
+	float *d_windows = nullptr;
+	DevSection *d_secs = nullptr;
+	DevCand *d_cands = nullptr;
+	size_t search_smem = 0, emit_smem = 0;
+};
+
+}  // namespace fb200
+
+using namespace fb200;
+
+struct fb200_encoder {
+	fb200_encoder_config cfg;  // resolved
+	int device = 0;
+	uint32_t max_blocks = 0;
+	std::map<int, Geometry> geoms;
+	// workspaces (sized for max_blocks blocks of cfg.blocksize)
+	int nsig = 0;
+	int32_t *d_sig = nullptr;
+	SigMeta *d_meta = nullptr;
+	int *d_blkflags = nullptr;
+	double *d_autoc = nullptr;
+	CandDesc *d_cdesc = nullptr;
+	SubframePlan *d_plans = nullptr;
+	uint8_t *d_slots = nullptr;
+	uint32_t *d_frame_bytes = nullptr;
+	uint32_t *d_chan_assign = nullptr;
+	unsigned long long *d_running = nullptr;
+	int *d_err = nullptr;
+	size_t max_nsec = 0, max_nslots = 0, lag_stride = 0;
+	// staging for the host entry point
+	int32_t *d_pcm = nullptr;
+	size_t d_pcm_cap = 0;
+	uint8_t *d_out = nullptr;
+	size_t d_out_cap = 0;
+	unsigned long long *d_offsets = nullptr;
+	size_t d_offsets_cap = 0;
+	cudaStream_t stream = nullptr;
+	uint64_t launches = 0;
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static size_t max_frame_bytes_for(const fb200_encoder_config &c, int bs)
+{
+	// header <= 16, per channel: verbatim worst case bs*(bps+1) bits + estimate slack bs/2 bits
+	// (count_rice_bits_in_partition_ underestimates by at most n/2) + warm-up/coefficients, CRC-16.
+	const size_t per_ch = ((size_t)bs * (c.bits_per_sample + 2) + 7) / 8 + 256;
+	return 16 + per_ch * c.channels + 2 + 16;
+}
+
+// Expand the apodization list into sections + candidates for blocksize bs
+// (apply_apodization_ / set_next_subdivide_tukey, stream_encoder.c:4293-4392).
+static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
+{
+	auto it = e->geoms.find(bs);
+	if(it != e->geoms.end()) { *out = &it->second; return FB200_OK; }
+	const fb200_encoder_config &c = e->cfg;
+	Geometry g;
+	g.bs = bs;
+	EncK &k = g.k;
+	memset(&k, 0, sizeof k);
+	k.channels = (int)c.channels; k.bps = (int)c.bits_per_sample; k.sample_rate = (int)c.sample_rate;
+	k.bs = bs; k.bs_stride = round_up((int)c.blocksize, 4);
+	k.do_ms = c.do_mid_side_stereo; k.loose_ms = c.loose_mid_side_stereo;
+	k.nsig = e->nsig;
+	k.max_order = (int)c.max_lpc_order >= bs ? bs - 1 : (int)c.max_lpc_order;
+	k.lags = k.max_order + 1;
+	k.lag_stride = (int)e->lag_stride;
+	k.qlp_precision = (int)c.qlp_coeff_precision;
+	k.exhaustive = c.do_exhaustive_model_search;
+	{   // stream_encoder.c:3759-3761, format.c:540-548
+		int o = 0, b = bs;
+		while(!(b & 1)) { o++; b >>= 1; }
+		if(o > 15) o = 15;
+		k.max_po = o < (int)c.max_residual_partition_order ? o : (int)c.max_residual_partition_order;
+		k.min_po = (int)c.min_residual_partition_order < k.max_po ? (int)c.min_residual_partition_order : k.max_po;
+	}
+	k.rice_limit = c.bits_per_sample > 16 ? (int)kRice2Escape : (int)kRiceEscape;
+	k.dis_const = c.disable_constant_subframes; k.dis_fixed = c.disable_fixed_subframes; k.dis_verb = c.disable_verbatim_subframes;
+	k.slot_stride = round_up((int)max_frame_bytes_for(c, (int)c.blocksize), 16);
+	k.slot_words = k.slot_stride / 4;
+
+	std::vector<float> windows;
+	std::vector<DevSection> secs;
+	std::vector<DevCand> cands;
+	if(k.max_order > 0 && bs > 1) {
+		for(uint32_t a = 0; a < c.num_apodizations; a++) {
+			const fb200_apodization &ap = c.apodizations[a];
+			const int win_off = (int)windows.size();
+			windows.resize(windows.size() + bs);
+			window_tukey(windows.data() + win_off, bs, ap.p);  // resize_buffers_, stream_encoder.c:2956-2967
+			const int root = (int)secs.size();
+			secs.push_back(DevSection{win_off, 0, bs, 0, 0});
+			cands.push_back(DevCand{0, root, root});
+			if(ap.type == FB200_APOD_SUBDIVIDE_TUKEY) {
+				for(int b = 2; b <= ap.parts; b++) {
+					if(bs / b <= FB200_MAX_LPC_ORDER) continue;  // :4349-4357
+					const int nparts = (b == 2) ? 2 : b;
+					for(int part = 0; part < nparts; part++) {
+						const int sidx = (int)secs.size();
+						secs.push_back(DevSection{win_off, 1, bs / b, bs / b / 2, (part * bs) / b});
+						cands.push_back(DevCand{0, sidx, root});
+						if(b != 2) cands.push_back(DevCand{1, sidx, root});  // depth 2 has no punch-outs (:4295-4302)
+					}
+				}
+			}
+		}
+	}
+	k.nsec = (int)secs.size();
+	k.nwin = (int)cands.size();
+	k.nslots = k.nwin * (k.exhaustive ? (k.max_order > 0 ? k.max_order : 1) : 1);
+	if((size_t)k.nsec > e->max_nsec || (size_t)k.nslots > e->max_nslots) {
+		set_error("internal: geometry for blocksize %d exceeds workspace (nsec %d/%zu nslots %d/%zu)", bs, k.nsec, e->max_nsec, k.nslots, e->max_nslots);
+		return FB200_ERR_INVALID;
+	}
+	if(!windows.empty()) {
+		FB_CUDA(cudaMalloc(&g.d_windows, windows.size() * sizeof(float)));
+		FB_CUDA(cudaMemcpy(g.d_windows, windows.data(), windows.size() * sizeof(float), cudaMemcpyHostToDevice));
+		FB_CUDA(cudaMalloc(&g.d_secs, secs.size() * sizeof(DevSection)));
+		FB_CUDA(cudaMemcpy(g.d_secs, secs.data(), secs.size() * sizeof(DevSection), cudaMemcpyHostToDevice));
+		FB_CUDA(cudaMalloc(&g.d_cands, cands.size() * sizeof(DevCand)));
+		FB_CUDA(cudaMemcpy(g.d_cands, cands.data(), cands.size() * sizeof(DevCand), cudaMemcpyHostToDevice));
+	}
+	g.search_smem = (size_t)k.bs_stride * 8;
+	{
+		const int xcap = k.bs_stride + (k.bs_stride >> 5) + 1;
+		g.emit_smem = (size_t)xcap * 8 + (size_t)k.slot_words * 4;
+	}
+	e->geoms[bs] = g;
+	*out = &e->geoms[bs];
+	return FB200_OK;
+}
+
+template <int LAGS>
+static void launch_autoc(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
+{
+	const int total = nitems * k.nsec;
+	k_autoc<LAGS><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
+}
+
+// Enqueue the whole pipeline for nb blocks of size g.bs starting at d_pcm.
+static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int nb, uint32_t first_frame, uint64_t frame_index0,
+                      uint8_t *d_out, size_t out_cap, unsigned long long *d_offsets, cudaStream_t st)
+{
+	EncK k = g.k;
+	k.first_frame = first_frame;
+	const int nitems = nb * k.nsig;
+	k_prep<<<nb, 256, 0, st>>>(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags);
+	e->launches++;
+	if(k.nwin > 0) {
+		if(k.lags <= 7) launch_autoc<7>(k, e, g, nitems, st);
+		else if(k.lags <= 9) launch_autoc<9>(k, e, g, nitems, st);
+		else if(k.lags <= 13) launch_autoc<13>(k, e, g, nitems, st);
+		else if(k.lags <= 17) launch_autoc<17>(k, e, g, nitems, st);
+		else launch_autoc<33>(k, e, g, nitems, st);
+		const int total = nitems * k.nwin;
+		k_lpc<<<(total + 127) / 128, 128, 0, st>>>(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems);
+		e->launches += 2;
+	}
+	k_search<<<nitems, 128, g.search_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
+	k_emit<<<nb, 256, g.emit_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
+	k_scan<<<1, 1024, 0, st>>>(e->d_frame_bytes, nb, d_offsets + frame_index0, e->d_running);
+	k_gather<<<nb, 256, 0, st>>>(k, e->d_slots, e->d_frame_bytes, d_offsets + frame_index0, d_out, (unsigned long long)out_cap, e->d_err);
+	e->launches += 4;
+	FB_CUDA(cudaGetLastError());
+	return FB200_OK;
+}
+
+extern "C" {
+
+const char *fb200_version(void) { return "flac_b200 0.1 (sm_100a)"; }
+const char *fb200_last_error(void) { return fb200::get_error(); }
+
+int fb200_device_count(void)
+{
+	int n = 0;
+	const cudaError_t e = cudaGetDeviceCount(&n);
+	if(e != cudaSuccess) {
+		set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+		return FB200_ERR_CUDA;
+	}
+	return n;
+}
+
+int fb200_encoder_config_preset(fb200_encoder_config *cfg, uint32_t channels, uint32_t bps, uint32_t sample_rate, uint32_t level, uint32_t blocksize)
+{
+	// src/libFLAC/stream_encoder.c:117-140 compression_levels_
+	static const struct { int ms, loose; uint32_t lpc, maxpo; int parts; } L[9] = {
+		{0, 0, 0, 3, 0}, {1, 1, 0, 3, 0}, {1, 0, 0, 3, 0}, {0, 0, 6, 4, 0}, {1, 1, 8, 4, 0},
+		{1, 0, 8, 5, 0}, {1, 0, 8, 6, 2}, {1, 0, 12, 6, 2}, {1, 0, 12, 6, 3}};
+	if(!cfg) return FB200_ERR_INVALID;
+	if(level > 8) level = 8;
+	memset(cfg, 0, sizeof *cfg);
+	cfg->channels = channels; cfg->bits_per_sample = bps; cfg->sample_rate = sample_rate; cfg->blocksize = blocksize;
+	cfg->do_mid_side_stereo = L[level].ms; cfg->loose_mid_side_stereo = L[level].loose;
+	cfg->max_lpc_order = L[level].lpc;
+	cfg->max_residual_partition_order = L[level].maxpo;
+	cfg->num_apodizations = 1;
+	if(L[level].parts) {
+		const float p = 5e-1;  // stream_encoder.c:2040-2049
+		cfg->apodizations[0].type = FB200_APOD_SUBDIVIDE_TUKEY;
+		cfg->apodizations[0].parts = L[level].parts;
+		cfg->apodizations[0].p = p / L[level].parts;
+	}
+	else {
+		cfg->apodizations[0].type = FB200_APOD_TUKEY;
+		cfg->apodizations[0].p = 0.5f;
+	}
+	return FB200_OK;
+}
+
+int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_t max_blocks, fb200_encoder **out)
+{
+	if(!cfg_in || !out) return FB200_ERR_INVALID;
+	*out = nullptr;
+	fb200_encoder_config c = *cfg_in;
+	// ---- init_stream_internal_ validation / defaults (stream_encoder.c:725-830)
+	if(c.channels == 0 || c.channels > FB200_MAX_CHANNELS) { set_error("invalid number of channels %u", c.channels); return FB200_ERR_INVALID; }
+	if(c.channels != 2) { c.do_mid_side_stereo = 0; c.loose_mid_side_stereo = 0; }
+	else if(!c.do_mid_side_stereo) c.loose_mid_side_stereo = 0;
+	if(c.bits_per_sample < 4 || c.bits_per_sample > 32) { set_error("invalid bits per sample %u", c.bits_per_sample); return FB200_ERR_INVALID; }
+	if(c.bits_per_sample > 24) { set_error("bits_per_sample %u > 24 (33-bit side channel path) is outside this engine's scope", c.bits_per_sample); return FB200_ERR_UNSUPPORTED; }
+	if(c.sample_rate == 0 || c.sample_rate > 1048575u) { set_error("invalid sample rate %u", c.sample_rate); return FB200_ERR_INVALID; }
+	if(c.blocksize == 0) c.blocksize = c.max_lpc_order == 0 ? 1152 : 4096;
+	if(c.blocksize < 16 || c.blocksize > 65535) { set_error("invalid blocksize %u", c.blocksize); return FB200_ERR_INVALID; }
+	if(c.max_lpc_order > FB200_MAX_LPC_ORDER) { set_error("invalid max LPC order %u", c.max_lpc_order); return FB200_ERR_INVALID; }
+	if(c.blocksize < c.max_lpc_order) { set_error("blocksize too small for LPC order"); return FB200_ERR_INVALID; }
+	if(c.qlp_coeff_precision == 0) {
+		if(c.bits_per_sample < 16) {
+			const uint32_t v = 2 + c.bits_per_sample / 2;
+			c.qlp_coeff_precision = v > kMinQlpPrecision ? v : kMinQlpPrecision;
+		}
+		else if(c.bits_per_sample == 16) {
+			if(c.blocksize <= 192) c.qlp_coeff_precision = 7;
+			else if(c.blocksize <= 384) c.qlp_coeff_precision = 8;
+			else if(c.blocksize <= 576) c.qlp_coeff_precision = 9;
+			else if(c.blocksize <= 1152) c.qlp_coeff_precision = 10;
+			else if(c.blocksize <= 2304) c.qlp_coeff_precision = 11;
+			else if(c.blocksize <= 4608) c.qlp_coeff_precision = 12;
+			else c.qlp_coeff_precision = 13;
+		}
+		else {
+			if(c.blocksize <= 384) c.qlp_coeff_precision = kMaxQlpPrecision - 2;
+			else if(c.blocksize <= 1152) c.qlp_coeff_precision = kMaxQlpPrecision - 1;
+			else c.qlp_coeff_precision = kMaxQlpPrecision;
+		}
+	}
+	else if(c.qlp_coeff_precision < kMinQlpPrecision || c.qlp_coeff_precision > kMaxQlpPrecision) { set_error("invalid qlp coeff precision %u", c.qlp_coeff_precision); return FB200_ERR_INVALID; }
+	if(c.max_residual_partition_order >= (1u << kRiceOrderLen)) c.max_residual_partition_order = (1u << kRiceOrderLen) - 1;
+	if(c.min_residual_partition_order >= c.max_residual_partition_order) c.min_residual_partition_order = c.max_residual_partition_order;
+	// ---- engine scope (fail loudly, no fallback)
+	if(c.max_residual_partition_order > (uint32_t)kMaxPartitionOrder) { set_error("max_residual_partition_order %u > %d unsupported", c.max_residual_partition_order, kMaxPartitionOrder); return FB200_ERR_UNSUPPORTED; }
+	if(c.do_qlp_coeff_prec_search) { set_error("qlp coeff precision search unsupported"); return FB200_ERR_UNSUPPORTED; }
+	if(c.limit_min_bitrate) { set_error("limit_min_bitrate unsupported"); return FB200_ERR_UNSUPPORTED; }
+	if(c.num_apodizations == 0 || c.num_apodizations > FB200_MAX_APODIZATIONS) { set_error("invalid number of apodizations"); return FB200_ERR_INVALID; }
+	for(uint32_t a = 0; a < c.num_apodizations; a++)
+		if(c.apodizations[a].type != FB200_APOD_TUKEY && c.apodizations[a].type != FB200_APOD_SUBDIVIDE_TUKEY) { set_error("apodization type %d unsupported", c.apodizations[a].type); return FB200_ERR_UNSUPPORTED; }
+
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		set_error("no CUDA device: the FLAC block engine has no CPU fallback");
+		return FB200_ERR_CUDA;
+	}
+	if(device < 0 || device >= ndev) { set_error("invalid device %d", device); return FB200_ERR_INVALID; }
+	FB_CUDA(cudaSetDevice(device));
+
+	fb200_encoder *e = new fb200_encoder();
+	e->cfg = c;
+	e->device = device;
+	e->max_blocks = max_blocks ? max_blocks : 4096;
+	e->nsig = (int)c.channels + ((c.channels == 2 && c.do_mid_side_stereo) ? 2 : 0);
+	{
+		const int lags = (int)c.max_lpc_order + 1;
+		e->lag_stride = lags <= 7 ? 7 : lags <= 9 ? 9 : lags <= 13 ? 13 : lags <= 17 ? 17 : 33;
+		size_t nsec = 0, nwin = 0;
+		for(uint32_t a = 0; a < c.num_apodizations; a++) {
+			nsec++; nwin++;
+			if(c.apodizations[a].type == FB200_APOD_SUBDIVIDE_TUKEY)
+				for(int b = 2; b <= c.apodizations[a].parts; b++) {
+					const int np = (b == 2) ? 2 : b;
+					nsec += np;
+					nwin += (b == 2) ? np : 2 * np;
+				}
+		}
+		e->max_nsec = nsec;
+		e->max_nslots = nwin * (c.do_exhaustive_model_search ? (c.max_lpc_order ? c.max_lpc_order : 1) : 1);
+	}
+	const size_t nb = e->max_blocks, nitems = nb * e->nsig;
+	const size_t bs_stride = (size_t)round_up((int)c.blocksize, 4);
+	const size_t slot = (size_t)round_up((int)max_frame_bytes_for(c, (int)c.blocksize), 16);
+#define ALLOC(ptr, bytes)                                                                     \
+	do {                                                                                      \
+		if(cudaMalloc(&(ptr), (bytes)) != cudaSuccess) {                                      \
+			set_error("cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(cudaGetLastError())); \
+			fb200_encoder_destroy(e);                                                         \
+			return FB200_ERR_ALLOC;                                                           \
+		}                                                                                     \
+	} while(0)
+	ALLOC(e->d_sig, nitems * bs_stride * sizeof(int32_t));
+	ALLOC(e->d_meta, nitems * sizeof(SigMeta));
+	ALLOC(e->d_blkflags, nb * sizeof(int));
+	ALLOC(e->d_autoc, (e->max_nsec ? e->max_nsec : 1) * nitems * e->lag_stride * sizeof(double));
+	ALLOC(e->d_cdesc, (e->max_nslots ? e->max_nslots : 1) * nitems * sizeof(CandDesc));
+	ALLOC(e->d_plans, nitems * sizeof(SubframePlan));
+	ALLOC(e->d_slots, nb * slot);
+	ALLOC(e->d_frame_bytes, nb * sizeof(uint32_t));
+	ALLOC(e->d_chan_assign, nb * sizeof(uint32_t));
+	ALLOC(e->d_running, sizeof(unsigned long long));
+	ALLOC(e->d_err, sizeof(int));
+#undef ALLOC
+	if(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		set_error("cudaStreamCreate failed");
+		fb200_encoder_destroy(e);
+		return FB200_ERR_CUDA;
+	}
+	// shared memory opt-in for the two big kernels
+	Geometry *g = nullptr;
+	int rc = build_geometry(e, (int)c.blocksize, &g);
+	if(rc != FB200_OK) { fb200_encoder_destroy(e); return rc; }
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	if(g->search_smem + 8192 > prop.sharedMemPerBlockOptin || g->emit_smem + 4096 > prop.sharedMemPerBlockOptin) {
+		set_error("blocksize %u x %u channels needs more shared memory than the device offers (search %zu, emit %zu)", c.blocksize, c.channels, g->search_smem, g->emit_smem);
+		fb200_encoder_destroy(e);
+		return FB200_ERR_UNSUPPORTED;
+	}
+	cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->search_smem);
+	cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->emit_smem);
+	*out = e;
+	return FB200_OK;
+}
+
+void fb200_encoder_destroy(fb200_encoder *e)
+{
+	if(!e) return;
+	cudaSetDevice(e->device);
+	for(auto &kv : e->geoms) {
+		cudaFree(kv.second.d_windows); cudaFree(kv.second.d_secs); cudaFree(kv.second.d_cands);
+	}
+	cudaFree(e->d_sig); cudaFree(e->d_meta); cudaFree(e->d_blkflags); cudaFree(e->d_autoc); cudaFree(e->d_cdesc);
+	cudaFree(e->d_plans); cudaFree(e->d_slots); cudaFree(e->d_frame_bytes); cudaFree(e->d_chan_assign);
+	cudaFree(e->d_running); cudaFree(e->d_err);
+	cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_offsets);
+	if(e->stream) cudaStreamDestroy(e->stream);
+	delete e;
+}
+
+int fb200_encoder_get_config(const fb200_encoder *e, fb200_encoder_config *resolved)
+{
+	if(!e || !resolved) return FB200_ERR_INVALID;
+	*resolved = e->cfg;
+	return FB200_OK;
+}
+
+size_t fb200_encoder_max_frame_bytes(const fb200_encoder *e) { return e ? max_frame_bytes_for(e->cfg, (int)e->cfg.blocksize) : 0; }
+uint64_t fb200_encoder_launch_count(const fb200_encoder *e) { return e ? e->launches : 0; }
+
+int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples, uint32_t first_frame_number,
+                        uint8_t *d_out, size_t out_capacity, uint64_t *d_frame_offsets, uint32_t *nframes,
+                        uint64_t *total_bytes, void *cuda_stream, int sync)
+{
+	if(!e || !d_pcm || !d_out || !d_frame_offsets) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(e->device));
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	const uint32_t bs = e->cfg.blocksize, ch = e->cfg.channels;
+	const uint64_t nfull = samples / bs;
+	const uint32_t tail = (uint32_t)(samples % bs);
+	if(nframes) *nframes = (uint32_t)(nfull + (tail ? 1 : 0));
+	FB_CUDA(cudaMemsetAsync(e->d_running, 0, sizeof(unsigned long long), st));
+	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
+	unsigned long long *offs = reinterpret_cast<unsigned long long *>(d_frame_offsets);
+	if(samples == 0) FB_CUDA(cudaMemsetAsync(offs, 0, sizeof(unsigned long long), st));
+	Geometry *g = nullptr;
+	int rc;
+	uint64_t done = 0;
+	while(done < nfull) {
+		const int nb = (int)((nfull - done) < e->max_blocks ? (nfull - done) : e->max_blocks);
+		if((rc = build_geometry(e, (int)bs, &g)) != FB200_OK) return rc;
+		if((rc = run_blocks(e, *g, d_pcm + done * bs * ch, nb, first_frame_number + (uint32_t)done, done, d_out, out_capacity, offs, st)) != FB200_OK) return rc;
+		done += nb;
+	}
+	if(tail) {
+		// last, short block: own window tables and header blocksize (stream_encoder.c:1703-1711)
+		if((rc = build_geometry(e, (int)tail, &g)) != FB200_OK) return rc;
+		if((rc = run_blocks(e, *g, d_pcm + nfull * bs * ch, 1, first_frame_number + (uint32_t)nfull, nfull, d_out, out_capacity, offs, st)) != FB200_OK) return rc;
+	}
+	if(sync) {
+		FB_CUDA(cudaStreamSynchronize(st));
+		int err = 0;
+		unsigned long long total = 0;
+		FB_CUDA(cudaMemcpy(&err, e->d_err, sizeof err, cudaMemcpyDeviceToHost));
+		FB_CUDA(cudaMemcpy(&total, e->d_running, sizeof total, cudaMemcpyDeviceToHost));
+		if(total_bytes) *total_bytes = total;
+		if(err) { set_error("output buffer too small"); return FB200_ERR_OUTPUT_TOO_SMALL; }
+	}
+	return FB200_OK;
+}
+
+int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, uint32_t first_frame_number,
+                      uint8_t *out, size_t out_capacity, uint64_t *frame_offsets, uint32_t *nframes)
+{
+	if(!e || (!pcm && samples) || !out || !frame_offsets) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(e->device));
+	const uint32_t bs = e->cfg.blocksize, ch = e->cfg.channels;
+	const uint64_t nfr = (samples + bs - 1) / bs;
+	const size_t pcm_bytes = (size_t)samples * ch * sizeof(int32_t);
+	const size_t need_out = (size_t)nfr * max_frame_bytes_for(e->cfg, (int)bs) + 64;
+	if(pcm_bytes > e->d_pcm_cap) {
+		cudaFree(e->d_pcm); e->d_pcm = nullptr; e->d_pcm_cap = 0;
+		FB_CUDA(cudaMalloc(&e->d_pcm, pcm_bytes + 256));
+		e->d_pcm_cap = pcm_bytes + 256;
+	}
+	if(need_out > e->d_out_cap) {
+		cudaFree(e->d_out); e->d_out = nullptr; e->d_out_cap = 0;
+		FB_CUDA(cudaMalloc(&e->d_out, need_out));
+		e->d_out_cap = need_out;
+	}
+	if((nfr + 1) > e->d_offsets_cap) {
+		cudaFree(e->d_offsets); e->d_offsets = nullptr; e->d_offsets_cap = 0;
+		FB_CUDA(cudaMalloc(&e->d_offsets, (nfr + 1) * sizeof(unsigned long long)));
+		e->d_offsets_cap = nfr + 1;
+	}
+	if(pcm_bytes) FB_CUDA(cudaMemcpyAsync(e->d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->stream));
+	uint64_t total = 0;
+	uint32_t nf = 0;
+	const int rc = fb200_encode_device(e, e->d_pcm, samples, first_frame_number, e->d_out, e->d_out_cap,
+	                                   reinterpret_cast<uint64_t *>(e->d_offsets), &nf, &total, e->stream, 1);
+	if(rc != FB200_OK) return rc;
+	if(nframes) *nframes = nf;
+	if(total > out_capacity) { set_error("output buffer too small: need %llu bytes", (unsigned long long)total); return FB200_ERR_OUTPUT_TOO_SMALL; }
+	FB_CUDA(cudaMemcpyAsync(out, e->d_out, total, cudaMemcpyDeviceToHost, e->stream));
+	FB_CUDA(cudaMemcpyAsync(frame_offsets, e->d_offsets, (nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+	FB_CUDA(cudaStreamSynchronize(e->stream));
+	return FB200_OK;
+}
+
+// ---- debug/stage-level access for the parity tests (plans of the last launch) ----
+int fb200_debug_copy_plans(fb200_encoder *e, uint32_t nblocks, void *host_plans, size_t plan_bytes, uint32_t *host_chan_assign)
+{
+	if(!e || !host_plans) return FB200_ERR_INVALID;
+	if(plan_bytes != sizeof(SubframePlan)) { set_error("plan size mismatch %zu != %zu", plan_bytes, sizeof(SubframePlan)); return FB200_ERR_INVALID; }
+	FB_CUDA(cudaSetDevice(e->device));
+	FB_CUDA(cudaDeviceSynchronize());
+	FB_CUDA(cudaMemcpy(host_plans, e->d_plans, (size_t)nblocks * e->nsig * sizeof(SubframePlan), cudaMemcpyDeviceToHost));
+	if(host_chan_assign) FB_CUDA(cudaMemcpy(host_chan_assign, e->d_chan_assign, nblocks * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return FB200_OK;
+}
+
+}  // extern "C"

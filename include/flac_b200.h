@@ -1,0 +1,148 @@
+/*
+ * flac_b200.h -- C ABI of the B200-native FLAC block engine (libflac_b200.so).
+ *
+ * Plain pointers and sizes only. This is the boundary the reference's per-frame hot path
+ * is replaced at: everything libFLAC does between "a blocksize worth of samples is
+ * buffered" and "the frame bytes are handed to the write callback"
+ *   reference: process_frame_ -> process_subframes_ -> add_subframe_ -> CRC-16
+ *              (src/libFLAC/stream_encoder.c:3435-3480, 3747-4043)
+ * and, for decode, between "frame bytes located" and "PCM handed to the write callback"
+ *   reference: read_frame_ (src/libFLAC/stream_decoder.c:2373-2622).
+ *
+ * The FLAC__stream_encoder_* / FLAC__stream_decoder_* object API (include/flac_b200_stream.h)
+ * is implemented in host C++ on top of these entry points.
+ *
+ * All functions return 0 on success or a negative FB200_ERR_* code; there is no CPU
+ * fallback: without a CUDA device every compute entry point fails with FB200_ERR_CUDA.
+ */
+#ifndef FLAC_B200_H
+#define FLAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_MAX_CHANNELS 8
+#define FB200_MAX_LPC_ORDER 32
+#define FB200_MAX_APODIZATIONS 32
+
+enum {
+	FB200_OK = 0,
+	FB200_ERR_CUDA = -1,          /* no device / CUDA runtime failure (see fb200_last_error) */
+	FB200_ERR_UNSUPPORTED = -2,   /* legal FLAC setting outside this engine's scope; fails loudly, no fallback */
+	FB200_ERR_INVALID = -3,       /* illegal argument (mirrors FLAC__StreamEncoderInitStatus rejections) */
+	FB200_ERR_OUTPUT_TOO_SMALL = -4,
+	FB200_ERR_BAD_STREAM = -5,    /* decoder: sync/CRC/parse error in a frame */
+	FB200_ERR_ALLOC = -6
+};
+
+/* Apodization functions (reference: FLAC__stream_encoder_set_apodization,
+ * src/libFLAC/stream_encoder.c:1939-2065; window generators src/libFLAC/window.c). */
+enum { FB200_APOD_TUKEY = 0, FB200_APOD_SUBDIVIDE_TUKEY = 1 };
+
+typedef struct {
+	int32_t type;   /* FB200_APOD_* */
+	float p;        /* tukey(p); for subdivide_tukey(n/p) this is p/n as the reference stores it (:2049) */
+	int32_t parts;  /* subdivide_tukey parts */
+} fb200_apodization;
+
+/* One field per FLAC__stream_encoder_set_* knob that reaches the per-frame path
+ * (include/FLAC/stream_encoder.h:738-1289; defaults src/libFLAC/stream_encoder.c:2630-2660). */
+typedef struct {
+	uint32_t channels;                      /* set_channels           1..8 */
+	uint32_t bits_per_sample;               /* set_bits_per_sample    4..24 (25..32 -> FB200_ERR_UNSUPPORTED) */
+	uint32_t sample_rate;                   /* set_sample_rate */
+	uint32_t blocksize;                     /* set_blocksize          0 = reference default (1152 / 4096) */
+	int32_t do_mid_side_stereo;             /* set_do_mid_side_stereo */
+	int32_t loose_mid_side_stereo;          /* set_loose_mid_side_stereo */
+	uint32_t max_lpc_order;                 /* set_max_lpc_order      0..32 */
+	uint32_t qlp_coeff_precision;           /* set_qlp_coeff_precision 0 = reference default */
+	int32_t do_qlp_coeff_prec_search;       /* set_do_qlp_coeff_prec_search (1 -> FB200_ERR_UNSUPPORTED) */
+	int32_t do_exhaustive_model_search;     /* set_do_exhaustive_model_search */
+	uint32_t min_residual_partition_order;  /* set_min_residual_partition_order */
+	uint32_t max_residual_partition_order;  /* set_max_residual_partition_order (<= 8) */
+	uint32_t num_apodizations;
+	fb200_apodization apodizations[FB200_MAX_APODIZATIONS];
+	int32_t disable_constant_subframes;     /* FLAC__stream_encoder_disable_constant_subframes (share/private.h:41) */
+	int32_t disable_fixed_subframes;        /* ..._disable_fixed_subframes */
+	int32_t disable_verbatim_subframes;     /* ..._disable_verbatim_subframes */
+	int32_t limit_min_bitrate;              /* set_limit_min_bitrate (1 -> FB200_ERR_UNSUPPORTED) */
+} fb200_encoder_config;
+
+typedef struct fb200_encoder fb200_encoder;
+typedef struct fb200_decoder fb200_decoder;
+
+/* ---- library ---- */
+const char *fb200_version(void);
+const char *fb200_last_error(void);          /* thread-local description of the last failure */
+int fb200_device_count(void);                /* <0: FB200_ERR_CUDA */
+
+/* ---- encoder ----
+ * fb200_encoder_config_preset == FLAC__stream_encoder_set_compression_level
+ * (stream_encoder.c:117-140, 1873-1904) plus set_channels/bits_per_sample/sample_rate/blocksize. */
+int fb200_encoder_config_preset(fb200_encoder_config *cfg, uint32_t channels, uint32_t bits_per_sample,
+                                uint32_t sample_rate, uint32_t compression_level, uint32_t blocksize);
+
+/* Validates like init_stream_internal_ (stream_encoder.c:725-830), resolves blocksize and
+ * qlp precision defaults, uploads window tables, sizes device workspaces for up to
+ * max_blocks_per_launch blocks (0 = default). */
+int fb200_encoder_create(const fb200_encoder_config *cfg, int device, uint32_t max_blocks_per_launch, fb200_encoder **out);
+void fb200_encoder_destroy(fb200_encoder *enc);
+int fb200_encoder_get_config(const fb200_encoder *enc, fb200_encoder_config *resolved);
+/* Upper bound for one frame in bytes (verbatim worst case), for sizing output buffers. */
+size_t fb200_encoder_max_frame_bytes(const fb200_encoder *enc);
+
+/*
+ * Encode `samples` samples per channel of interleaved, sign-extended int32 PCM
+ * (the layout of FLAC__stream_encoder_process_interleaved, include/FLAC/stream_encoder.h:1896)
+ * as consecutive frames of `blocksize` samples, the last one short, numbered from
+ * first_frame_number. Frames are written back to back into `out`; frame i occupies
+ * [frame_offsets[i], frame_offsets[i+1]) and *nframes = ceil(samples / blocksize).
+ * frame_offsets must hold *nframes + 1 entries.
+ *
+ * _host:   pcm/out/frame_offsets are HOST pointers; H2D and D2H copies happen inside.
+ * _device: pcm/out/frame_offsets are DEVICE pointers on the encoder's device; kernels are
+ *          enqueued on `cuda_stream` (a cudaStream_t, may be NULL) and the call returns after
+ *          enqueueing unless `sync` is non-zero. total_bytes (host, optional) needs sync.
+ */
+int fb200_encode_host(fb200_encoder *enc, const int32_t *pcm_interleaved, uint64_t samples,
+                      uint32_t first_frame_number, uint8_t *out, size_t out_capacity,
+                      uint64_t *frame_offsets, uint32_t *nframes);
+
+int fb200_encode_device(fb200_encoder *enc, const int32_t *d_pcm_interleaved, uint64_t samples,
+                        uint32_t first_frame_number, uint8_t *d_out, size_t out_capacity,
+                        uint64_t *d_frame_offsets, uint32_t *nframes, uint64_t *total_bytes,
+                        void *cuda_stream, int sync);
+
+/* Number of kernel launches issued by this encoder so far (bench.py's gpu_launches). */
+uint64_t fb200_encoder_launch_count(const fb200_encoder *enc);
+
+/* ---- decoder ----
+ * Batch frame decode (read_frame_ for many frames). The caller supplies frame boundaries
+ * (frames carry no length field) and the STREAMINFO facts. Every frame must
+ * have `blocksize` samples except the last, which may be shorter. Output is interleaved
+ * int32 PCM, frame i at sample offset i*blocksize. */
+typedef struct {
+	uint32_t channels, bits_per_sample, sample_rate, blocksize;
+} fb200_decoder_config;
+
+int fb200_decoder_create(const fb200_decoder_config *cfg, int device, uint32_t max_frames_per_launch, fb200_decoder **out);
+void fb200_decoder_destroy(fb200_decoder *dec);
+
+int fb200_decode_host(fb200_decoder *dec, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
+                      int32_t *pcm_interleaved, uint64_t pcm_capacity_samples, uint64_t *samples_decoded,
+                      uint32_t *bad_frames);
+
+int fb200_decode_device(fb200_decoder *dec, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,
+                        int32_t *d_pcm_interleaved, uint64_t pcm_capacity_samples, uint32_t *d_frame_status,
+                        void *cuda_stream, int sync);
+
+uint64_t fb200_decoder_launch_count(const fb200_decoder *dec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAC_B200_H */

@@ -1,0 +1,160 @@
+"""GPU parity tests proper: the CUDA encode path (through the C ABI, host buffers) against
+ (1) the CPU restatement oracle/flac_oracle.c, and
+ (2) the compiled reference libFLAC (oracle/_ref/*.so) when it travelled to this box,
+frame by frame, bit-exact."""
+import numpy as np
+import pytest
+
+import oraclelib
+import reflib
+import signals
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_frames(x, bps, rate, level, bs=0, **over):
+    import flac_b200
+    enc = flac_b200.Encoder(flac_b200.preset(x.shape[1], bps, rate, level, bs, **over))
+    try:
+        return enc.encode_frames(x)
+    finally:
+        enc.close()
+
+
+def _oracle_frames(x, bps, rate, level, bs=0, **over):
+    enc = oraclelib.Encoder(oraclelib.preset(x.shape[1], bps, rate, level, bs, **over))
+    return enc.encode_stream(x)
+
+
+def _assert_same(got, want, what):
+    assert len(got) == len(want), f"{what}: frame count {len(got)} != {len(want)}"
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, f"{what}: {len(bad)}/{len(want)} frames differ, first {bad[:5]}"
+
+
+@pytest.mark.parametrize("level", range(9))
+def test_levels_16bit_stereo_vs_oracle_and_reference(level):
+    x = signals.music_like(4096 * 10 + 777, 2, 16, 44100, seed=1)
+    got = _gpu_frames(x, 16, 44100, level)
+    _assert_same(got, _oracle_frames(x, 16, 44100, level), "oracle")
+    if reflib.available("default"):
+        for variant in ("strict", "default"):
+            _, _, ref = reflib.encode(x, 16, rate=44100, level=level, variant=variant)
+            _assert_same(got, ref, f"reference[{variant}]")
+
+
+@pytest.mark.parametrize("level", [0, 3, 5, 8])
+@pytest.mark.parametrize("ch,bps,rate", [(1, 16, 44100), (2, 24, 96000), (8, 24, 192000), (3, 20, 48000), (2, 8, 22050), (1, 12, 8000)])
+def test_depths_and_channel_counts(level, ch, bps, rate):
+    x = signals.music_like(4096 * 3 + 123, ch, bps, rate, seed=11 + ch)
+    got = _gpu_frames(x, bps, rate, level)
+    _assert_same(got, _oracle_frames(x, bps, rate, level), "oracle")
+    if reflib.available("default"):
+        _, _, ref = reflib.encode(x, bps, rate=rate, level=level)
+        _assert_same(got, ref, "reference[default]")
+
+
+@pytest.mark.parametrize("bs", [16, 17, 32, 33, 192, 256, 576, 1000, 1152, 2304, 4608, 8192])
+@pytest.mark.parametrize("level", [2, 5, 8])
+def test_blocksizes(bs, level):
+    x = signals.music_like(max(3 * bs + bs // 3, 600), 2, 16, 44100, seed=3)
+    got = _gpu_frames(x, 16, 44100, level, bs)
+    _assert_same(got, _oracle_frames(x, 16, 44100, level, bs), "oracle")
+
+
+STRESS = {
+    "white_noise_fs": lambda: signals.white_noise(4096 * 3, 2, 16, seed=5),
+    "white_noise_24": lambda: signals.white_noise(4096 * 3, 2, 24, seed=6),
+    "silence": lambda: signals.silence(4096 * 3 + 5, 2),
+    "dc": lambda: signals.dc(4096 * 3, 2, 1234),
+    "dc_mono_neg": lambda: signals.dc(5000, 1, -32768),
+    "wasted3": lambda: signals.wasted_bits(4096 * 3, 2, 16, 3),
+    "fsd": lambda: signals.full_scale_deflection(4096 * 2, 2, 16, 7),
+    "noisy_sine": lambda: signals.noisy_sine(4096 * 3, 2, 16),
+    "quiet_noise": lambda: signals.white_noise(4096 * 2, 2, 16, seed=9, scale=0.0002),
+    "two_tone": lambda: signals.sine(4096 * 4, 1, 16, 44100, freq=1000.0, freq2=1001.3),
+    "sine24": lambda: signals.sine(4096 * 3, 2, 24, 96000, freq=997.0),
+    "left_only": lambda: np.ascontiguousarray(np.stack([signals.music_like(9000, 1, 16, seed=4)[:, 0], np.zeros(9000, np.int32)], axis=1)),
+    "identical_lr": lambda: np.ascontiguousarray(np.repeat(signals.music_like(9000, 1, 16, seed=4), 2, axis=1)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STRESS))
+@pytest.mark.parametrize("level", [1, 5, 8])
+def test_stress_inputs(name, level):
+    x = STRESS[name]()
+    bps = 24 if name.endswith("24") else 16
+    got = _gpu_frames(x, bps, 44100, level)
+    _assert_same(got, _oracle_frames(x, bps, 44100, level), "oracle")
+    if reflib.available("strict"):
+        _, _, ref = reflib.encode(x, bps, rate=44100, level=level, variant="strict")
+        _assert_same(got, ref, "reference[strict]")
+
+
+def test_option_matrix():
+    x = signals.music_like(4096 * 3 + 99, 2, 16, 44100, seed=2)
+    cases = [
+        (dict(do_exhaustive_model_search=1), dict(do_exhaustive_model_search=1), 5),
+        (dict(do_exhaustive_model_search=1), dict(do_exhaustive_model_search=1), 8),
+        (dict(do_mid_side_stereo=0), dict(do_mid_side=0), 8),
+        (dict(loose_mid_side_stereo=1), dict(loose_mid_side=1), 8),
+        (dict(max_lpc_order=32), dict(max_lpc_order=32), 8),
+        (dict(qlp_coeff_precision=9), dict(qlp_coeff_precision=9), 5),
+        (dict(min_residual_partition_order=2, max_residual_partition_order=8), dict(min_residual_partition_order=2, max_residual_partition_order=8), 5),
+        (dict(disable_constant_subframes=1), dict(disable_constant_subframes=1), 5),
+        (dict(disable_fixed_subframes=1), dict(disable_fixed_subframes=1), 5),
+        (dict(disable_verbatim_subframes=1), dict(disable_verbatim_subframes=1), 0),
+    ]
+    for gpu_kw, or_kw, level in cases:
+        got = _gpu_frames(x, 16, 44100, level, **gpu_kw)
+        _assert_same(got, _oracle_frames(x, 16, 44100, level, **or_kw), str(gpu_kw))
+
+
+def test_multi_launch_chunking_and_frame_numbers():
+    """More blocks than one launch holds + a non-zero first frame number (UTF-8 header widths)."""
+    import flac_b200
+    x = signals.music_like(1152 * 23 + 5, 2, 16, 44100, seed=8)
+    enc = flac_b200.Encoder(flac_b200.preset(2, 16, 44100, 2), max_blocks_per_launch=4)
+    stream, offs = enc.encode(x, first_frame_number=0)
+    want = _oracle_frames(x, 16, 44100, 2)
+    got = [stream[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(offs) - 1)]
+    _assert_same(got, want, "chunked")
+    # large frame numbers: compare single frames against the oracle at that number
+    o = oraclelib.Encoder(oraclelib.preset(2, 16, 44100, 2))
+    for first in (127, 128, 2047, 2048, 65535, 65536, 0x1FFFFF, 0x200000, 0x3FFFFFF, 0x4000000, 0x7FFFFFF0):
+        g = enc.encode_frames(x[:1152 * 2], first_frame_number=first)
+        for j in range(2):
+            assert g[j] == o.encode_frame(x[1152 * j:1152 * (j + 1)], first + j), f"frame number {first + j}"
+    enc.close()
+
+
+def test_reference_decoder_accepts_gpu_stream():
+    """flac -t equivalent: the reference decoder decodes our frames (behind a reference-made
+    stream header) to the original PCM with no errors."""
+    if not reflib.available("default"):
+        pytest.skip("oracle/_ref not present")
+    for ch, bps, level in ((2, 16, 8), (2, 24, 8), (1, 16, 5), (8, 24, 5)):
+        x = signals.music_like(4096 * 3 + 50, ch, bps, 48000, seed=31)
+        stream, hdr, _ = reflib.encode(x, bps, rate=48000, level=level)
+        mine = b"".join(_gpu_frames(x, bps, 48000, level))
+        y, info = reflib.decode(stream[:hdr] + mine, x.shape[0], ch)
+        assert info[3] == 0 and np.array_equal(x, y)
+
+
+def test_big_batch_property_round_trip():
+    """BASELINE cfg2-sized property check (10 000 blocks stereo 16-bit -5): every frame decodes
+    (oracle decoder on a sample of frames, CRC-16 verified) back to the input."""
+    import flac_b200
+    nblocks = 10000
+    base = signals.music_like(4096 * 50, 2, 16, 44100, seed=1)
+    x = np.ascontiguousarray(np.tile(base, (nblocks // 50, 1)))
+    x[::7, 0] ^= 1  # break the periodicity a little
+    enc = flac_b200.Encoder(flac_b200.preset(2, 16, 44100, 5), max_blocks_per_launch=4096)
+    stream, offs = enc.encode(x)
+    assert len(offs) == nblocks + 1
+    rng = np.random.default_rng(0)
+    for i in rng.choice(nblocks, 200, replace=False):
+        fr = stream[int(offs[i]):int(offs[i + 1])].tobytes()
+        y = oraclelib.decode_frames(fr, 2, 16, 44100, 4096)
+        assert np.array_equal(y, x[i * 4096:(i + 1) * 4096]), f"frame {i}"
+    enc.close()
