@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the FLAC block-encode hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg2_l8|cfg3] [--impl reference]
+
+One "step" = one pass of the hot path over one batch (BASELINE configs: 10 000 blocks of 4096
+samples). Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the definitions:
+  value      whole-job Msamples/s (samples = blocks x blocksize x channels), inputs resident in HBM,
+             CUDA events on the launching stream, max over ranks.
+  e2e        the same through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H inside.
+  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events
+             recorded between the kernels in the timed region) against the measured HBM peak.
+  cpu_baseline  the compiled reference libFLAC (oracle/_ref) on this box's host cores.
+--impl reference times the reference's own CPU implementation (all host threads) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (channels, bps, rate, level, blocks, blocksize, description)
+    "cfg2": (2, 16, 44100, 5, 10000, 4096, "stereo 16-bit 44.1 kHz, -5, 10 000 blocks of 4096 (BASELINE configs[1])"),
+    "cfg2_l8": (2, 16, 44100, 8, 10000, 4096, "stereo 16-bit 44.1 kHz, -8, 10 000 blocks of 4096 (target config)"),
+    "cfg3": (2, 24, 96000, 8, 10000, 4096, "stereo 24-bit 96 kHz, -8, 10 000 blocks of 4096 (BASELINE configs[2])"),
+}
+
+
+def make_pcm(ch, bps, rate, blocks, bs, seed):
+    """Music-like base of 256 blocks, tiled, plus independent +-1 LSB dither so that
+    no two frames are identical. Deterministic in `seed`."""
+    import signals
+    base_blocks = min(256, blocks)
+    base = signals.music_like(base_blocks * bs, ch, bps, rate, seed=seed).astype(np.int32)
+    reps = (blocks + base_blocks - 1) // base_blocks
+    x = np.tile(base, (reps, 1))[: blocks * bs]
+    rng = np.random.default_rng(seed + 12345)
+    x = x + rng.integers(-1, 2, size=x.shape, dtype=np.int8)
+    lim = (1 << (bps - 1)) - 1
+    np.clip(x, -lim - 1, lim, out=x)
+    return np.ascontiguousarray(x.astype(np.int32))
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        with open(self.f.name) as fh:
+            for line in fh:
+                parts = [s.strip() for s in line.split(",")]
+                if len(parts) >= 9:
+                    rows.append(parts)
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = []
+        reasons = set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # "under load" = samples in the upper half of the observed range
+            hi = [v for v in sm if v >= 0.5 * max(sm)]
+            out["sm_mhz"] = float(np.median(hi))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return {}
+
+
+def host_threads():
+    return max(1, min(os.cpu_count() or 1, 64))  # FLAC__STREAM_ENCODER_MAX_THREADS = 64
+
+
+def run_reference(x, bps, rate, level, threads, steps, warmup):
+    import reflib
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        reflib.encode(x, bps, rate=rate, level=level, threads=threads, md5=False, want_bytes=False)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=0, help="override the number of blocks (debug)")
+    ap.add_argument("--kernels-only", action="store_true", help="profiling aid: device-resident steps only (no e2e, no CPU baseline)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ch, bps, rate, level, blocks, bs, desc = WORKLOADS[args.workload]
+    if args.blocks:
+        blocks = args.blocks
+    samples_per_step = blocks * bs * ch
+    config = {"workload": f"{args.workload}: {desc}", "channels": ch, "bits_per_sample": bps, "sample_rate": rate,
+              "compression_level": level, "blocks_per_gpu_per_step": blocks, "blocksize": bs,
+              "sharding": f"{world} rank(s) x independent block ranges, no data-path collective",
+              "l2_policy": "inputs (%.0f MB int32/step/GPU) exceed the 126 MB L2" % (samples_per_step * 4 / 1e6)}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        nthreads = host_threads()
+        sample_blocks = min(blocks, 2500 if level >= 6 else 5000)
+        x = make_pcm(ch, bps, rate, sample_blocks, bs, seed=1)
+        times = run_reference(x, bps, rate, level, nthreads, args.steps, args.warmup)
+        ms = 1e3 * sum(times) / len(times)
+        val = sample_blocks * bs * ch / (ms / 1e3) / 1e6
+        sample = f"{sample_blocks} blocks of the workload per step, reference libFLAC 1.5.0 (oracle/_ref, shipped flags), num_threads={nthreads}, MD5 off, in-memory callbacks"
+        line = {"impl": "reference", "metric": "encode_msamples_per_s", "value": round(val, 3), "unit": "Msamples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": round(val, 3), "unit": "Msamples/s", "cores": nthreads, "kind": "reference", "sample": sample},
+                "e2e": {"value": round(val, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import flac_b200
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: flac_b200 has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # every rank owns its own block range (different seed -> different "files")
+    x = make_pcm(ch, bps, rate, blocks, bs, seed=1 + rank)
+    nsamp = x.shape[0]
+    h_pcm = torch.empty(x.shape, dtype=torch.int32, pin_memory=True)
+    h_pcm.numpy()[:] = x
+    d_pcm = h_pcm.to("cuda", non_blocking=False)
+
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), device=local_rank, max_blocks_per_launch=4096)
+    out_cap = blocks * enc.max_frame_bytes + 64
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device="cuda")
+    d_offs = torch.empty(blocks + 1, dtype=torch.int64, device="cuda")
+    h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
+    h_offs = torch.empty(blocks + 1, dtype=torch.int64, pin_memory=True)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        enc.encode_device(d_pcm.data_ptr(), nsamp, d_out.data_ptr(), out_cap, d_offs.data_ptr(), 0, stream.cuda_stream, sync=False)
+
+    def step_host():
+        s, o = enc.encode(h_pcm.numpy(), 0, out=h_out.numpy(), offsets=h_offs.numpy().view(np.uint64))
+        return s, o
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    total_bytes = int(d_offs[blocks].item())
+
+    # ---- timed region 1: device-resident (value) with per-kernel events
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    enc.set_profiling(True)
+    enc.profile(reset=True)
+    launches0 = enc.launches
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = enc.launches - launches0
+    prof = enc.profile(reset=True)
+    enc.set_profiling(False)
+
+    if args.kernels_only:
+        print(json.dumps({"kernels_only": True, "ms_per_step": dev_ms / args.steps, "profile": prof}))
+        return 0
+
+    # ---- timed region 2: end to end through the host-buffer C ABI
+    for _ in range(2):
+        step_host()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s_host, o_host = step_host()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_samples = sum_over_ranks(float(samples_per_step))  # per step, all ranks
+    value = total_samples * args.steps / (dev_ms / 1e3) / 1e6
+    e2e_value = total_samples * args.steps / e2e_s / 1e6
+
+    # ---- quick in-run integrity check of the e2e output (frame sizes consistent)
+    assert int(o_host[blocks]) == total_bytes, "device and host paths disagree on stream size"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline (rank 0's kernels)
+    peak, peak_src = peaks()
+    nsig = enc.nsig
+    frame_bytes = total_bytes / blocks
+    per_block_bytes = {
+        "k_prep": 4 * bs * ch + 4 * bs * nsig,
+        "k_autoc": 4 * bs * nsig,
+        "k_lpc": 0,
+        "k_search": 4 * bs * nsig,
+        "k_emit": 4 * bs * ch + frame_bytes,
+        "k_scan": 12,
+        "k_gather": 2 * frame_bytes,
+    }
+    traffic = ncu_traffic().get(args.workload, {})
+    total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        if n == 0:
+            continue
+        blocks_per_launch = blocks * args.steps / n
+        alg = per_block_bytes[name] * blocks_per_launch
+        avg_ms = ms / n
+        kernels[name] = {"ms_per_launch": round(avg_ms, 4), "launches": n, "share": round(ms / total_kernel_ms, 4),
+                         "alg_bytes_per_launch": int(alg), "achieved_gbs": round(alg / (avg_ms * 1e-3) / 1e9, 2),
+                         "frac": round(alg / (avg_ms * 1e-3) / 1e9 / peak, 4)}
+    dominant = max(kernels, key=lambda k: kernels[k]["share"])
+    dk = kernels[dominant]
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
+                "traffic": traffic.get(dominant), "peak_source": peak_src, "share_of_step": dk["share"],
+                "pipeline": {"alg_bytes_per_step": int((4 * bs * ch + frame_bytes) * blocks),
+                             "achieved_gbs": round((4 * bs * ch + frame_bytes) * blocks * args.steps / (dev_ms * 1e-3) / 1e9, 2)},
+                "kernels": kernels}
+
+    # ---- CPU baseline: compiled reference on the host cores, bounded sample
+    cpu = None
+    try:
+        import reflib
+        if reflib.available("default"):
+            nthreads = host_threads()
+            sb = min(blocks, 1500 if level >= 6 else 4000)
+            xs = x[: sb * bs]
+            t1 = run_reference(xs[: (sb // 4) * bs], bps, rate, level, 1, 1, 1)
+            tn = run_reference(xs, bps, rate, level, nthreads, 2, 1)
+            v1 = (sb // 4) * bs * ch / (sum(t1) / len(t1)) / 1e6
+            vn = sb * bs * ch / (sum(tn) / len(tn)) / 1e6
+            cpu = {"value": round(vn, 3), "unit": "Msamples/s", "cores": nthreads, "kind": "reference",
+                   "value_1_thread": round(v1, 3),
+                   "sample": f"{sb} blocks of this workload (1-thread figure on {sb // 4}), reference libFLAC 1.5.0 built from /root/reference (oracle/_ref, shipped flags), MD5 off, in-memory callbacks"}
+    except Exception as ex:  # the baseline is reported, never required for the GPU number
+        cpu = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+
+    line = {
+        "metric": "encode_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+        "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(nsamp * ch * 4),
+                "d2h_bytes_per_step": int(total_bytes + 8 * (blocks + 1)), "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "bit_exact": "frames identical to reference libFLAC: tests/test_gpu_encode.py",
+        "compressed_bytes_per_step": total_bytes,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -89,6 +89,10 @@ def lib():
     L.fb200_encode_device.restype = C.c_int
     L.fb200_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p, C.c_int]
+    L.fb200_encoder_set_profiling.restype = C.c_int
+    L.fb200_encoder_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.fb200_encoder_get_profile.restype = C.c_int
+    L.fb200_encoder_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double * 7), C.POINTER(C.c_uint64 * 7), C.c_int]
     L.fb200_debug_copy_plans.restype = C.c_int
     L.fb200_debug_copy_plans.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
     if hasattr(L, "fb200_decoder_create"):
@@ -178,6 +182,18 @@ class Encoder:
         _check(lib().fb200_encode_device(self._h, d_pcm_ptr, samples, first_frame_number, d_out_ptr, out_capacity, d_offsets_ptr,
                                          C.byref(nf), C.byref(total), C.c_void_p(stream), 1 if sync else 0))
         return nf.value, (total.value if sync else None)
+
+    PROF_NAMES = ("k_prep", "k_autoc", "k_lpc", "k_search", "k_emit", "k_scan", "k_gather")
+
+    def set_profiling(self, on=True):
+        _check(lib().fb200_encoder_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self, reset=True):
+        """{kernel: (total_ms, launches)} from CUDA events recorded between the kernels."""
+        ms = (C.c_double * 7)()
+        n = (C.c_uint64 * 7)()
+        _check(lib().fb200_encoder_get_profile(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return {name: (ms[i], int(n[i])) for i, name in enumerate(self.PROF_NAMES)}
 
     def debug_plans(self, nblocks):
         plans = (SubframePlan * (nblocks * self.nsig))()

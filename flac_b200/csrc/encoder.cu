@@ -93,7 +93,40 @@ struct fb200_encoder {
 	size_t d_offsets_cap = 0;
 	cudaStream_t stream = nullptr;
 	uint64_t launches = 0;
+	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
+	bool prof_on = false;
+	std::vector<cudaEvent_t> prof_events;   // consecutive events; kernel id of the interval ending at event i in prof_ids[i]
+	std::vector<int> prof_ids;              // -1 = interval start
+	double prof_ms[FB200_PROF_KERNELS] = {0};
+	uint64_t prof_launches[FB200_PROF_KERNELS] = {0};
 };
+
+static void prof_mark(fb200_encoder *e, int id, cudaStream_t st)
+{
+	if(!e->prof_on) return;
+	cudaEvent_t ev;
+	if(cudaEventCreate(&ev) != cudaSuccess) return;
+	cudaEventRecord(ev, st);
+	e->prof_events.push_back(ev);
+	e->prof_ids.push_back(id);
+}
+
+static void prof_resolve(fb200_encoder *e)
+{
+	for(size_t i = 0; i < e->prof_events.size(); i++) {
+		if(e->prof_ids[i] >= 0 && i > 0) {
+			float ms = 0.f;
+			cudaEventSynchronize(e->prof_events[i]);
+			if(cudaEventElapsedTime(&ms, e->prof_events[i - 1], e->prof_events[i]) == cudaSuccess) {
+				e->prof_ms[e->prof_ids[i]] += ms;
+				e->prof_launches[e->prof_ids[i]]++;
+			}
+		}
+	}
+	for(cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+	e->prof_events.clear();
+	e->prof_ids.clear();
+}
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -202,7 +235,9 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 	EncK k = g.k;
 	k.first_frame = first_frame;
 	const int nitems = nb * k.nsig;
+	prof_mark(e, -1, st);
 	k_prep<<<nb, 256, 0, st>>>(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags);
+	prof_mark(e, FB200_PROF_PREP, st);
 	e->launches++;
 	if(k.nwin > 0) {
 		if(k.lags <= 7) launch_autoc<7>(k, e, g, nitems, st);
@@ -210,14 +245,20 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 		else if(k.lags <= 13) launch_autoc<13>(k, e, g, nitems, st);
 		else if(k.lags <= 17) launch_autoc<17>(k, e, g, nitems, st);
 		else launch_autoc<33>(k, e, g, nitems, st);
+		prof_mark(e, FB200_PROF_AUTOC, st);
 		const int total = nitems * k.nwin;
 		k_lpc<<<(total + 127) / 128, 128, 0, st>>>(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems);
+		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
 	k_search<<<nitems, 128, g.search_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
+	prof_mark(e, FB200_PROF_SEARCH, st);
 	k_emit<<<nb, 256, g.emit_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
+	prof_mark(e, FB200_PROF_EMIT, st);
 	k_scan<<<1, 1024, 0, st>>>(e->d_frame_bytes, nb, d_offsets + frame_index0, e->d_running);
+	prof_mark(e, FB200_PROF_SCAN, st);
 	k_gather<<<nb, 256, 0, st>>>(k, e->d_slots, e->d_frame_bytes, d_offsets + frame_index0, d_out, (unsigned long long)out_cap, e->d_err);
+	prof_mark(e, FB200_PROF_GATHER, st);
 	e->launches += 4;
 	FB_CUDA(cudaGetLastError());
 	return FB200_OK;
@@ -488,6 +529,28 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 	FB_CUDA(cudaMemcpyAsync(out, e->d_out, total, cudaMemcpyDeviceToHost, e->stream));
 	FB_CUDA(cudaMemcpyAsync(frame_offsets, e->d_offsets, (nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
 	FB_CUDA(cudaStreamSynchronize(e->stream));
+	return FB200_OK;
+}
+
+int fb200_encoder_set_profiling(fb200_encoder *e, int on)
+{
+	if(!e) return FB200_ERR_INVALID;
+	cudaSetDevice(e->device);
+	prof_resolve(e);
+	e->prof_on = on != 0;
+	return FB200_OK;
+}
+
+int fb200_encoder_get_profile(fb200_encoder *e, double ms[FB200_PROF_KERNELS], uint64_t launches[FB200_PROF_KERNELS], int reset)
+{
+	if(!e) return FB200_ERR_INVALID;
+	cudaSetDevice(e->device);
+	prof_resolve(e);
+	for(int i = 0; i < FB200_PROF_KERNELS; i++) {
+		if(ms) ms[i] = e->prof_ms[i];
+		if(launches) launches[i] = e->prof_launches[i];
+		if(reset) { e->prof_ms[i] = 0; e->prof_launches[i] = 0; }
+	}
 	return FB200_OK;
 }
 

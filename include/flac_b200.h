@@ -120,6 +120,17 @@ int fb200_encode_device(fb200_encoder *enc, const int32_t *d_pcm_interleaved, ui
 /* Number of kernel launches issued by this encoder so far (bench.py's gpu_launches). */
 uint64_t fb200_encoder_launch_count(const fb200_encoder *enc);
 
+/* Measurement support: per-kernel device time from CUDA events recorded on the launching
+ * stream between the kernels of every launch (off by default). Index = FB200_PROF_*. */
+enum { FB200_PROF_PREP = 0, FB200_PROF_AUTOC, FB200_PROF_LPC, FB200_PROF_SEARCH, FB200_PROF_EMIT,
+       FB200_PROF_SCAN, FB200_PROF_GATHER, FB200_PROF_KERNELS };
+int fb200_encoder_set_profiling(fb200_encoder *enc, int on);
+int fb200_encoder_get_profile(fb200_encoder *enc, double ms[FB200_PROF_KERNELS], uint64_t launches[FB200_PROF_KERNELS], int reset);
+
+/* Stage-level debug access used by the parity tests: the per-signal decisions (fb200::SubframePlan,
+ * flac_b200/csrc/fb200_internal.h) and channel assignments of the most recent launch. */
+int fb200_debug_copy_plans(fb200_encoder *enc, uint32_t nblocks, void *host_plans, size_t plan_bytes, uint32_t *host_chan_assign);
+
 /* ---- decoder ----
  * Batch frame decode (read_frame_ for many frames). The caller supplies frame boundaries
  * (frames carry no length field) and the STREAMINFO facts. Every frame must
