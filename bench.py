@@ -263,6 +263,8 @@ def main():
     enc.set_profiling(False)
 
     if args.kernels_only:
+        if rank == 0:
+            sampler.stop()
         print(json.dumps({"kernels_only": True, "ms_per_step": dev_ms / args.steps, "profile": prof}))
         return 0
 

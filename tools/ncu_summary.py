@@ -1,0 +1,56 @@
+"""Summarise an ncu report (.ncu-rep) into a small CSV/markdown under profiles/.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_prof_l8 [--blocks 4096]
+
+Writes <out>.csv (selected raw metrics per captured launch) and prints a table.
+"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    cols = [(m, hdr.index(m)) for m in METRICS if m in hdr]
+    kidx = hdr.index("Kernel Name")
+    with open(out + ".csv", "w", newline="") as fh:
+        w = csv.writer(fh)
+        w.writerow(["kernel"] + [f"{m} [{units[i]}]" for m, i in cols])
+        for r in rows[2:]:
+            w.writerow([r[kidx].split("(")[0]] + [r[i] for _, i in cols])
+    traffic = {}
+    for r in rows[2:]:
+        name = r[kidx].split("(")[0].replace("void ", "").split("<")[0]
+        def val(m):
+            i = hdr.index(m)
+            v = float(r[i])
+            u = units[i]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        traffic[name] = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+        print(f"{name:12s} dur {r[hdr.index('gpu__time_duration.sum')]} {units[hdr.index('gpu__time_duration.sum')]}  dram {traffic[name] / 1e6:.1f} MB  inst {r[hdr.index('smsp__inst_executed.sum')]}")
+    print(json.dumps(traffic))
+
+
+if __name__ == "__main__":
+    main()
