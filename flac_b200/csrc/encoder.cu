@@ -8,12 +8,13 @@
 // sections and LPC candidates. Everything per block runs in the kernels.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
 #include <vector>
 
-#include "encode_kernels.cuh"
+#include "encode_kernels_v2.cuh"
 
 namespace fb200 {
 
@@ -59,6 +60,9 @@ struct Geometry {
 	DevSection *d_secs = nullptr;
 	DevCand *d_cands = nullptr;
 	size_t search_smem = 0, emit_smem = 0;
+	size_t search2_smem = 0, emit2_smem = 0;
+	int fast_search = 0, fast_emit = 0;  // 0 = general kernels; emit: 256 / 128 = CTA width of the fast kernel
+	int maxord_t = 8;
 };
 
 }  // namespace fb200
@@ -93,6 +97,7 @@ struct fb200_encoder {
 	size_t d_offsets_cap = 0;
 	cudaStream_t stream = nullptr;
 	uint64_t launches = 0;
+	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
 	bool prof_on = false;
 	std::vector<cudaEvent_t> prof_events;   // consecutive events; kernel id of the interval ending at event i in prof_ids[i]
@@ -216,6 +221,16 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		const int xcap = k.bs_stride + (k.bs_stride >> 5) + 1;
 		g.emit_smem = (size_t)xcap * 8 + (size_t)k.slot_words * 4;
 	}
+	{
+		// fast-path eligibility (encode_kernels_v2.cuh)
+		const int xcap = k.bs_stride + (k.bs_stride >> 5) + 1;
+		g.maxord_t = k.max_order <= 8 ? 8 : k.max_order <= 12 ? 12 : 32;
+		g.fast_search = (bs % 128 == 0 && bs / 128 <= 36 && k.max_po <= 7) ? 1 : 0;
+		if(bs % 256 == 0 && bs / 256 <= 18) g.fast_emit = 256;
+		else if(bs % 128 == 0 && bs / 128 <= 36) g.fast_emit = 128;
+		g.search2_smem = (size_t)xcap * 4;
+		g.emit2_smem = (size_t)xcap * 4 + (size_t)k.slot_words * 4;
+	}
 	e->geoms[bs] = g;
 	*out = &e->geoms[bs];
 	return FB200_OK;
@@ -226,6 +241,40 @@ static void launch_autoc(const EncK &k, const fb200_encoder *e, const Geometry &
 {
 	const int total = nitems * k.nsec;
 	k_autoc<LAGS><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
+}
+
+template <int LAGS, int U>
+static void launch_autoc2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
+{
+	const int total = nitems * k.nsec;
+	k_autoc2<LAGS, U><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
+}
+
+template <int MO>
+static void launch_search2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
+{
+	if(k.bs / 128 == 32) k_search2<32, MO, true><<<nitems, 128, g.search2_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
+	else k_search2<36, MO, false><<<nitems, 128, g.search2_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
+}
+
+template <int MO>
+static void launch_emit2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nb, cudaStream_t st)
+{
+	if(g.fast_emit == 256) {
+		if(k.bs / 256 == 16) k_emit2<256, 16, MO, true><<<nb, 256, g.emit2_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
+		else k_emit2<256, 18, MO, false><<<nb, 256, g.emit2_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
+	}
+	else k_emit2<128, 36, MO, false><<<nb, 128, g.emit2_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
+}
+
+template <int MO>
+static void set_smem_attrs(int search_bytes, int emit_bytes)
+{
+	cudaFuncSetAttribute(k_search2<32, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
+	cudaFuncSetAttribute(k_search2<36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
+	cudaFuncSetAttribute(k_emit2<256, 16, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
+	cudaFuncSetAttribute(k_emit2<256, 18, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
+	cudaFuncSetAttribute(k_emit2<128, 36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
 }
 
 // Enqueue the whole pipeline for nb blocks of size g.bs starting at d_pcm.
@@ -240,20 +289,39 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 	prof_mark(e, FB200_PROF_PREP, st);
 	e->launches++;
 	if(k.nwin > 0) {
-		if(k.lags <= 7) launch_autoc<7>(k, e, g, nitems, st);
-		else if(k.lags <= 9) launch_autoc<9>(k, e, g, nitems, st);
-		else if(k.lags <= 13) launch_autoc<13>(k, e, g, nitems, st);
-		else if(k.lags <= 17) launch_autoc<17>(k, e, g, nitems, st);
-		else launch_autoc<33>(k, e, g, nitems, st);
+		if(e->use_v1) {
+			if(k.lags <= 7) launch_autoc<7>(k, e, g, nitems, st);
+			else if(k.lags <= 9) launch_autoc<9>(k, e, g, nitems, st);
+			else if(k.lags <= 13) launch_autoc<13>(k, e, g, nitems, st);
+			else if(k.lags <= 17) launch_autoc<17>(k, e, g, nitems, st);
+			else launch_autoc<33>(k, e, g, nitems, st);
+		}
+		else {
+			if(k.lags <= 7) launch_autoc2<7, 28>(k, e, g, nitems, st);
+			else if(k.lags <= 9) launch_autoc2<9, 36>(k, e, g, nitems, st);
+			else if(k.lags <= 13) launch_autoc2<13, 52>(k, e, g, nitems, st);
+			else if(k.lags <= 17) launch_autoc2<17, 68>(k, e, g, nitems, st);
+			else launch_autoc2<33, 132>(k, e, g, nitems, st);
+		}
 		prof_mark(e, FB200_PROF_AUTOC, st);
 		const int total = nitems * k.nwin;
 		k_lpc<<<(total + 127) / 128, 128, 0, st>>>(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems);
 		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
-	k_search<<<nitems, 128, g.search_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
+	if(g.fast_search && !e->use_v1) {
+		if(g.maxord_t == 8) launch_search2<8>(k, e, g, nitems, st);
+		else if(g.maxord_t == 12) launch_search2<12>(k, e, g, nitems, st);
+		else launch_search2<32>(k, e, g, nitems, st);
+	}
+	else k_search<<<nitems, 128, g.search_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
 	prof_mark(e, FB200_PROF_SEARCH, st);
-	k_emit<<<nb, 256, g.emit_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
+	if(g.fast_emit && !e->use_v1) {
+		if(g.maxord_t == 8) launch_emit2<8>(k, e, g, nb, st);
+		else if(g.maxord_t == 12) launch_emit2<12>(k, e, g, nb, st);
+		else launch_emit2<32>(k, e, g, nb, st);
+	}
+	else k_emit<<<nb, 256, g.emit_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
 	prof_mark(e, FB200_PROF_EMIT, st);
 	k_scan<<<1, 1024, 0, st>>>(e->d_frame_bytes, nb, d_offsets + frame_index0, e->d_running);
 	prof_mark(e, FB200_PROF_SCAN, st);
@@ -394,7 +462,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 			return FB200_ERR_ALLOC;                                                           \
 		}                                                                                     \
 	} while(0)
-	ALLOC(e->d_sig, nitems * bs_stride * sizeof(int32_t));
+	ALLOC(e->d_sig, (nitems * bs_stride + 1024) * sizeof(int32_t));  // + slack: k_autoc2 reads whole int4 bodies past the last run
 	ALLOC(e->d_meta, nitems * sizeof(SigMeta));
 	ALLOC(e->d_blkflags, nb * sizeof(int));
 	ALLOC(e->d_autoc, (e->max_nsec ? e->max_nsec : 1) * nitems * e->lag_stride * sizeof(double));
@@ -424,6 +492,13 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	}
 	cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->search_smem);
 	cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->emit_smem);
+	set_smem_attrs<8>((int)g->search2_smem, (int)g->emit2_smem);
+	set_smem_attrs<12>((int)g->search2_smem, (int)g->emit2_smem);
+	set_smem_attrs<32>((int)g->search2_smem, (int)g->emit2_smem);
+	{
+		const char *env = getenv("FB200_FORCE_GENERAL_KERNELS");
+		e->use_v1 = env && env[0] == '1';
+	}
 	*out = e;
 	return FB200_OK;
 }
