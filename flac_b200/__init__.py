@@ -107,6 +107,10 @@ def lib():
                                           C.c_void_p, C.c_int]
         L.fb200_decoder_launch_count.restype = C.c_uint64
         L.fb200_decoder_launch_count.argtypes = [C.c_void_p]
+        L.fb200_decoder_set_profiling.restype = C.c_int
+        L.fb200_decoder_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.fb200_decoder_get_profile.restype = C.c_int
+        L.fb200_decoder_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64 * 3), C.c_int]
     _lib = L
     return L
 
@@ -224,6 +228,17 @@ class Decoder:
     @property
     def launches(self):
         return int(lib().fb200_decoder_launch_count(self._h))
+
+    PROF_NAMES = ("k_dec_parse", "k_dec_crc", "k_dec_merge")
+
+    def set_profiling(self, on=True):
+        _check(lib().fb200_decoder_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self, reset=True):
+        ms = (C.c_double * 3)()
+        n = (C.c_uint64 * 3)()
+        _check(lib().fb200_decoder_get_profile(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return {name: (ms[i], int(n[i])) for i, name in enumerate(self.PROF_NAMES)}
 
     def decode(self, stream, offsets, total_samples=None):
         """stream: uint8 ndarray of back-to-back frames; offsets: uint64[nframes+1]. Returns int32 [samples, channels]."""

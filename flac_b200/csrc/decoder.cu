@@ -1,0 +1,220 @@
+// decoder.cu -- host side of the B200 FLAC batch frame decoder + its C ABI (include/flac_b200.h).
+#include <string.h>
+
+#include <vector>
+
+#include "decode_kernels.cuh"
+
+using namespace fb200;
+
+struct fb200_decoder {
+	fb200_decoder_config cfg;
+	int device = 0;
+	uint32_t max_frames = 0;
+	DecK k{};
+	int32_t *d_scratch = nullptr;
+	DecFrameMeta *d_meta = nullptr;
+	// staging for the host entry point
+	uint8_t *d_frames = nullptr;
+	size_t d_frames_cap = 0;
+	unsigned long long *d_offsets = nullptr;
+	size_t d_offsets_cap = 0;
+	int32_t *d_pcm = nullptr;
+	size_t d_pcm_cap = 0;
+	uint32_t *d_status = nullptr;
+	size_t d_status_cap = 0;
+	cudaStream_t stream = nullptr;
+	uint64_t launches = 0;
+	bool prof_on = false;
+	std::vector<cudaEvent_t> prof_events;
+	std::vector<int> prof_ids;
+	double prof_ms[FB200_DPROF_KERNELS] = {0};
+	uint64_t prof_launches[FB200_DPROF_KERNELS] = {0};
+};
+
+static void dprof_mark(fb200_decoder *d, int id, cudaStream_t st)
+{
+	if(!d->prof_on) return;
+	cudaEvent_t ev;
+	if(cudaEventCreate(&ev) != cudaSuccess) return;
+	cudaEventRecord(ev, st);
+	d->prof_events.push_back(ev);
+	d->prof_ids.push_back(id);
+}
+
+static void dprof_resolve(fb200_decoder *d)
+{
+	for(size_t i = 1; i < d->prof_events.size(); i++) {
+		if(d->prof_ids[i] < 0) continue;
+		float ms = 0.f;
+		cudaEventSynchronize(d->prof_events[i]);
+		if(cudaEventElapsedTime(&ms, d->prof_events[i - 1], d->prof_events[i]) == cudaSuccess) {
+			d->prof_ms[d->prof_ids[i]] += ms;
+			d->prof_launches[d->prof_ids[i]]++;
+		}
+	}
+	for(cudaEvent_t ev : d->prof_events) cudaEventDestroy(ev);
+	d->prof_events.clear();
+	d->prof_ids.clear();
+}
+
+extern "C" {
+
+int fb200_decoder_create(const fb200_decoder_config *cfg, int device, uint32_t max_frames, fb200_decoder **out)
+{
+	if(!cfg || !out) return FB200_ERR_INVALID;
+	*out = nullptr;
+	if(cfg->channels == 0 || cfg->channels > FB200_MAX_CHANNELS) { set_error("invalid number of channels %u", cfg->channels); return FB200_ERR_INVALID; }
+	if(cfg->bits_per_sample < 4 || cfg->bits_per_sample > 32) { set_error("invalid bits per sample %u", cfg->bits_per_sample); return FB200_ERR_INVALID; }
+	if(cfg->bits_per_sample > 24) { set_error("bits_per_sample %u > 24 is outside this engine's scope", cfg->bits_per_sample); return FB200_ERR_UNSUPPORTED; }
+	if(cfg->blocksize < 1 || cfg->blocksize > 65535) { set_error("invalid blocksize %u", cfg->blocksize); return FB200_ERR_INVALID; }
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		set_error("no CUDA device: the FLAC block engine has no CPU fallback");
+		return FB200_ERR_CUDA;
+	}
+	if(device < 0 || device >= ndev) { set_error("invalid device %d", device); return FB200_ERR_INVALID; }
+	FB_CUDA(cudaSetDevice(device));
+	fb200_decoder *d = new fb200_decoder();
+	d->cfg = *cfg;
+	d->device = device;
+	d->max_frames = max_frames ? max_frames : 16384;
+	d->k.channels = (int)cfg->channels; d->k.bps = (int)cfg->bits_per_sample; d->k.sample_rate = (int)cfg->sample_rate;
+	d->k.blocksize = (int)cfg->blocksize;
+	d->k.bs_stride = ((int)cfg->blocksize + 3) / 4 * 4;
+	if(cudaMalloc(&d->d_scratch, (size_t)d->max_frames * cfg->channels * d->k.bs_stride * sizeof(int32_t)) != cudaSuccess ||
+	   cudaMalloc(&d->d_meta, (size_t)d->max_frames * sizeof(DecFrameMeta)) != cudaSuccess ||
+	   cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		set_error("decoder workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+		fb200_decoder_destroy(d);
+		return FB200_ERR_ALLOC;
+	}
+	*out = d;
+	return FB200_OK;
+}
+
+void fb200_decoder_destroy(fb200_decoder *d)
+{
+	if(!d) return;
+	cudaSetDevice(d->device);
+	cudaFree(d->d_scratch); cudaFree(d->d_meta); cudaFree(d->d_frames); cudaFree(d->d_offsets); cudaFree(d->d_pcm); cudaFree(d->d_status);
+	if(d->stream) cudaStreamDestroy(d->stream);
+	delete d;
+}
+
+uint64_t fb200_decoder_launch_count(const fb200_decoder *d) { return d ? d->launches : 0; }
+
+int fb200_decoder_set_profiling(fb200_decoder *d, int on)
+{
+	if(!d) return FB200_ERR_INVALID;
+	cudaSetDevice(d->device);
+	dprof_resolve(d);
+	d->prof_on = on != 0;
+	return FB200_OK;
+}
+
+int fb200_decoder_get_profile(fb200_decoder *d, double ms[FB200_DPROF_KERNELS], uint64_t launches[FB200_DPROF_KERNELS], int reset)
+{
+	if(!d) return FB200_ERR_INVALID;
+	cudaSetDevice(d->device);
+	dprof_resolve(d);
+	for(int i = 0; i < FB200_DPROF_KERNELS; i++) {
+		if(ms) ms[i] = d->prof_ms[i];
+		if(launches) launches[i] = d->prof_launches[i];
+		if(reset) { d->prof_ms[i] = 0; d->prof_launches[i] = 0; }
+	}
+	return FB200_OK;
+}
+
+int fb200_decode_device(fb200_decoder *d, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,
+                        int32_t *d_pcm, uint64_t pcm_capacity_samples, uint32_t *d_frame_status, void *cuda_stream, int sync)
+{
+	if(!d || !d_frames || !d_frame_offsets || !d_pcm) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(d->device));
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	const unsigned long long *offs = reinterpret_cast<const unsigned long long *>(d_frame_offsets);
+	uint32_t done = 0;
+	while(done < nframes) {
+		const int nf = (int)((nframes - done) < d->max_frames ? (nframes - done) : d->max_frames);
+		// offsets are absolute into d_frames; output frame index is absolute too (done + i)
+		dprof_mark(d, -1, st);
+		k_dec_parse<<<(nf + 63) / 64, 64, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_scratch, d->d_meta);
+		dprof_mark(d, FB200_DPROF_PARSE, st);
+		k_dec_crc<<<(nf + 3) / 4, 128, 0, st>>>(d_frames, offs + done, nf, d->d_meta);
+		dprof_mark(d, FB200_DPROF_CRC, st);
+		k_dec_merge<<<nf, 256, 0, st>>>(d->k, d->d_scratch, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * d->cfg.channels,
+		                               pcm_capacity_samples - (unsigned long long)done * d->cfg.blocksize,
+		                               d_frame_status ? d_frame_status + done : nullptr);
+		dprof_mark(d, FB200_DPROF_MERGE, st);
+		d->launches += 3;
+		done += nf;
+	}
+	FB_CUDA(cudaGetLastError());
+	if(sync) FB_CUDA(cudaStreamSynchronize(st));
+	return FB200_OK;
+}
+
+int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
+                      int32_t *pcm, uint64_t pcm_capacity_samples, uint64_t *samples_decoded, uint32_t *bad_frames)
+{
+	if(!d || !frames || !frame_offsets || !pcm) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(d->device));
+	if(samples_decoded) *samples_decoded = 0;
+	if(bad_frames) *bad_frames = 0;
+	if(nframes == 0) return FB200_OK;
+	const size_t nbytes = (size_t)frame_offsets[nframes];
+	const uint64_t need_samples = (uint64_t)nframes * d->cfg.blocksize;
+	const uint64_t cap = pcm_capacity_samples < need_samples ? pcm_capacity_samples : need_samples;
+	if(nbytes + 64 > d->d_frames_cap) {
+		cudaFree(d->d_frames); d->d_frames = nullptr; d->d_frames_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_frames, nbytes + 64));
+		d->d_frames_cap = nbytes + 64;
+	}
+	if((size_t)nframes + 1 > d->d_offsets_cap) {
+		cudaFree(d->d_offsets); d->d_offsets = nullptr; d->d_offsets_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_offsets, ((size_t)nframes + 1) * sizeof(unsigned long long)));
+		d->d_offsets_cap = (size_t)nframes + 1;
+	}
+	if(need_samples * d->cfg.channels > d->d_pcm_cap) {
+		cudaFree(d->d_pcm); d->d_pcm = nullptr; d->d_pcm_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_pcm, need_samples * d->cfg.channels * sizeof(int32_t)));
+		d->d_pcm_cap = need_samples * d->cfg.channels;
+	}
+	if(nframes > d->d_status_cap) {
+		cudaFree(d->d_status); d->d_status = nullptr; d->d_status_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_status, (size_t)nframes * sizeof(uint32_t)));
+		d->d_status_cap = nframes;
+	}
+	FB_CUDA(cudaMemcpyAsync(d->d_frames, frames, nbytes, cudaMemcpyHostToDevice, d->stream));
+	FB_CUDA(cudaMemsetAsync(d->d_frames + nbytes, 0, 64, d->stream));
+	FB_CUDA(cudaMemcpyAsync(d->d_offsets, frame_offsets, ((size_t)nframes + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d->stream));
+	const int rc = fb200_decode_device(d, d->d_frames, reinterpret_cast<const uint64_t *>(d->d_offsets), nframes, d->d_pcm, need_samples,
+	                                   d->d_status, d->stream, 0);
+	if(rc != FB200_OK) return rc;
+	FB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm, (size_t)cap * d->cfg.channels * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+	uint32_t *h_status = new uint32_t[nframes];
+	cudaError_t ce = cudaMemcpyAsync(h_status, d->d_status, (size_t)nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream);
+	if(ce == cudaSuccess) ce = cudaStreamSynchronize(d->stream);
+	if(ce != cudaSuccess) {
+		delete[] h_status;
+		set_error("decode: %s", cudaGetErrorString(ce));
+		return FB200_ERR_CUDA;
+	}
+	uint32_t bad = 0, first_bad = 0, first_code = 0;
+	for(uint32_t i = 0; i < nframes; i++)
+		if((h_status[i] & 0xffu) != DEC_OK) {
+			if(!bad) { first_bad = i; first_code = h_status[i] & 0xffu; }
+			bad++;
+		}
+	const uint64_t last_bs = h_status[nframes - 1] >> 8;
+	delete[] h_status;
+	if(bad_frames) *bad_frames = bad;
+	if(samples_decoded) {
+		const uint64_t n = (uint64_t)(nframes - 1) * d->cfg.blocksize + last_bs;
+		*samples_decoded = n < cap ? n : cap;
+	}
+	if(bad) set_error("%u of %u frames failed to decode (first: frame %u, status %u)", bad, nframes, first_bad, first_code);
+	return FB200_OK;
+}
+
+}  // extern "C"

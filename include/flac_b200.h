@@ -147,11 +147,17 @@ int fb200_decode_host(fb200_decoder *dec, const uint8_t *frames, const uint64_t 
                       int32_t *pcm_interleaved, uint64_t pcm_capacity_samples, uint64_t *samples_decoded,
                       uint32_t *bad_frames);
 
+/* _device: d_frames must be readable 8 bytes past the last frame (the bit reader fetches whole
+ * words); d_frame_status[i] = status (low byte, 0 = ok) | decoded blocksize << 8. */
 int fb200_decode_device(fb200_decoder *dec, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,
                         int32_t *d_pcm_interleaved, uint64_t pcm_capacity_samples, uint32_t *d_frame_status,
                         void *cuda_stream, int sync);
 
 uint64_t fb200_decoder_launch_count(const fb200_decoder *dec);
+
+enum { FB200_DPROF_PARSE = 0, FB200_DPROF_CRC, FB200_DPROF_MERGE, FB200_DPROF_KERNELS };
+int fb200_decoder_set_profiling(fb200_decoder *dec, int on);
+int fb200_decoder_get_profile(fb200_decoder *dec, double ms[FB200_DPROF_KERNELS], uint64_t launches[FB200_DPROF_KERNELS], int reset);
 
 #ifdef __cplusplus
 }
