@@ -32,6 +32,7 @@ WORKLOADS = {
     "cfg2": (2, 16, 44100, 5, 10000, 4096, "stereo 16-bit 44.1 kHz, -5, 10 000 blocks of 4096 (BASELINE configs[1])"),
     "cfg2_l8": (2, 16, 44100, 8, 10000, 4096, "stereo 16-bit 44.1 kHz, -8, 10 000 blocks of 4096 (target config)"),
     "cfg3": (2, 24, 96000, 8, 10000, 4096, "stereo 24-bit 96 kHz, -8, 10 000 blocks of 4096 (BASELINE configs[2])"),
+    "cfg5": (2, 16, 44100, 8, 100000, 4096, "decode-only: 100 000 pre-encoded -8 stereo 16-bit frames, offsets supplied (BASELINE configs[4])"),
 }
 
 
@@ -137,6 +138,140 @@ def run_reference(x, bps, rate, level, threads, steps, warmup):
     return times
 
 
+def bench_decode(args, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks, config):
+    """Decode-only workload: frames are produced once by our (bit-exact) encoder, then the timed
+    region decodes them: value = device-resident, e2e = host buffers through fb200_decode_host."""
+    import torch
+    import flac_b200
+    ch, bps, rate, level, blocks, bs, desc = WORKLOADS[args.workload]
+    if args.blocks:
+        blocks = args.blocks
+    x = make_pcm(ch, bps, rate, blocks, bs, seed=1 + rank)
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), device=local_rank, max_blocks_per_launch=4096)
+    stream_np, offs_np = enc.encode(x)
+    enc.close()
+    total_bytes = int(offs_np[blocks])
+    h_stream = torch.empty(total_bytes + 64, dtype=torch.uint8, pin_memory=True)
+    h_stream.numpy()[:total_bytes] = stream_np
+    h_stream.numpy()[total_bytes:] = 0
+    h_offs = torch.empty(blocks + 1, dtype=torch.int64, pin_memory=True)
+    h_offs.numpy()[:] = offs_np.view(np.int64)
+    d_stream = h_stream.to("cuda")
+    d_offs = h_offs.to("cuda")
+    d_pcm = torch.empty((blocks * bs, ch), dtype=torch.int32, device="cuda")
+    d_status = torch.empty(blocks, dtype=torch.int32, device="cuda")
+    h_pcm = torch.empty((blocks * bs, ch), dtype=torch.int32, pin_memory=True)
+    dec = flac_b200.Decoder(ch, bps, rate, bs, device=local_rank, max_frames_per_launch=32768)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        dec.decode_device(d_stream.data_ptr(), d_offs.data_ptr(), blocks, d_pcm.data_ptr(), blocks * bs, d_status.data_ptr(), stream.cuda_stream)
+
+    import ctypes as C
+
+    def step_host():
+        ns, bad = C.c_uint64(0), C.c_uint32(0)
+        rc = flac_b200.lib().fb200_decode_host(dec._h, h_stream.data_ptr(), h_offs.data_ptr(), blocks, h_pcm.data_ptr(), blocks * bs, C.byref(ns), C.byref(bad))
+        assert rc == 0 and bad.value == 0
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    assert int((d_status & 0xff).sum().item()) == 0, "decode errors"
+    assert torch.equal(d_pcm.cpu(), torch.from_numpy(x)), "decoded PCM differs from the input"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dec.set_profiling(True)
+    dec.profile(reset=True)
+    launches0 = dec.launches
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = dec.launches - launches0
+    prof = dec.profile(reset=True)
+    dec.set_profiling(False)
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.array_equal(h_pcm.numpy(), x), "e2e decoded PCM differs from the input"
+
+    samples_per_step = blocks * bs * ch
+    total_samples = sum_over_ranks(float(samples_per_step))
+    value = total_samples * args.steps / (dev_ms / 1e3) / 1e6
+    e2e_value = total_samples * args.steps / e2e_s / 1e6
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    frame_bytes = total_bytes / blocks
+    per_frame = {"k_dec_parse": frame_bytes + 4 * bs * ch, "k_dec_crc": frame_bytes, "k_dec_merge": 8 * bs * ch}
+    total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        if n == 0:
+            continue
+        alg = per_frame[name] * blocks * args.steps / n
+        avg_ms = ms / n
+        kernels[name] = {"ms_per_launch": round(avg_ms, 4), "launches": n, "share": round(ms / total_kernel_ms, 4),
+                         "alg_bytes_per_launch": int(alg), "achieved_gbs": round(alg / (avg_ms * 1e-3) / 1e9, 2),
+                         "frac": round(alg / (avg_ms * 1e-3) / 1e9 / peak, 4)}
+    dominant = max(kernels, key=lambda k: kernels[k]["share"])
+    dk = kernels[dominant]
+    traffic = ncu_traffic().get(args.workload, {})
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
+                "traffic": traffic.get(dominant), "peak_source": peak_src, "share_of_step": dk["share"],
+                "pipeline": {"alg_bytes_per_step": int((frame_bytes + 4 * bs * ch) * blocks),
+                             "achieved_gbs": round((frame_bytes + 4 * bs * ch) * blocks * args.steps / (dev_ms * 1e-3) / 1e9, 2)},
+                "kernels": kernels}
+    cpu = None
+    try:
+        import reflib
+        if reflib.available("default"):
+            sb = 2000
+            xs = x[: sb * bs]
+            ref_stream, _, _ = reflib.encode(xs, bps, rate=rate, level=level)
+            t = []
+            for i in range(3):
+                t0 = time.perf_counter()
+                y, info = reflib.decode(ref_stream, sb * bs, ch)
+                t.append(time.perf_counter() - t0)
+            v1 = sb * bs * ch / min(t[1:]) / 1e6
+            cpu = {"value": round(v1, 3), "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                   "sample": f"{sb} frames of this workload, reference libFLAC 1.5.0 stream decoder (single-threaded by design), MD5 off, in-memory callbacks"}
+    except Exception as ex:
+        cpu = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
+    line = {
+        "metric": "decode_msamples_per_s", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+        "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(total_bytes + 8 * (blocks + 1)),
+                "d2h_bytes_per_step": int(samples_per_step * 4 + 4 * blocks), "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "bit_exact": "decoded PCM == input asserted in this run (device and e2e paths)",
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,13 +301,34 @@ def main():
         if rank != 0:
             return 0
         nthreads = host_threads()
-        sample_blocks = min(blocks, 2500 if level >= 6 else 5000)
-        x = make_pcm(ch, bps, rate, sample_blocks, bs, seed=1)
-        times = run_reference(x, bps, rate, level, nthreads, args.steps, args.warmup)
-        ms = 1e3 * sum(times) / len(times)
-        val = sample_blocks * bs * ch / (ms / 1e3) / 1e6
-        sample = f"{sample_blocks} blocks of the workload per step, reference libFLAC 1.5.0 (oracle/_ref, shipped flags), num_threads={nthreads}, MD5 off, in-memory callbacks"
-        line = {"impl": "reference", "metric": "encode_msamples_per_s", "value": round(val, 3), "unit": "Msamples/s", "n_gpus": args.gpus,
+        if args.workload == "cfg5":
+            # the reference decoder is single-threaded per stream; use every host core by decoding
+            # one stream per thread (ctypes releases the GIL), as a many-file batch would
+            import reflib
+            from concurrent.futures import ThreadPoolExecutor
+            sample_blocks = 500
+            x = make_pcm(ch, bps, rate, sample_blocks, bs, seed=1)
+            ref_stream, _, _ = reflib.encode(x, bps, rate=rate, level=level)
+            times = []
+            with ThreadPoolExecutor(nthreads) as pool:
+                for i in range(args.warmup + args.steps):
+                    t0 = time.perf_counter()
+                    list(pool.map(lambda _: reflib.decode(ref_stream, sample_blocks * bs, ch)[0].shape, range(nthreads)))
+                    if i >= args.warmup:
+                        times.append(time.perf_counter() - t0)
+            ms = 1e3 * sum(times) / len(times)
+            val = nthreads * sample_blocks * bs * ch / (ms / 1e3) / 1e6
+            sample = f"{nthreads} streams x {sample_blocks} frames per step, one reference libFLAC 1.5.0 stream decoder per host thread, MD5 off, in-memory callbacks"
+            metric = "decode_msamples_per_s"
+        else:
+            sample_blocks = min(blocks, 2500 if level >= 6 else 5000)
+            x = make_pcm(ch, bps, rate, sample_blocks, bs, seed=1)
+            times = run_reference(x, bps, rate, level, nthreads, args.steps, args.warmup)
+            ms = 1e3 * sum(times) / len(times)
+            val = sample_blocks * bs * ch / (ms / 1e3) / 1e6
+            sample = f"{sample_blocks} blocks of the workload per step, reference libFLAC 1.5.0 (oracle/_ref, shipped flags), num_threads={nthreads}, MD5 off, in-memory callbacks"
+            metric = "encode_msamples_per_s"
+        line = {"impl": "reference", "metric": metric, "value": round(val, 3), "unit": "Msamples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": round(val, 3), "unit": "Msamples/s", "cores": nthreads, "kind": "reference", "sample": sample},
@@ -212,6 +368,9 @@ def main():
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    if args.workload == "cfg5":
+        return bench_decode(args, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks, config)
 
     # every rank owns its own block range (different seed -> different "files")
     x = make_pcm(ch, bps, rate, blocks, bs, seed=1 + rank)
