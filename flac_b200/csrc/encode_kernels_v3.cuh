@@ -1,0 +1,343 @@
+// encode_kernels_v3.cuh -- k_search3: one WARP per (block, signal).
+//
+// The v2 search kernel spends a large part of its time at block barriers (3 warps/SMSP, two
+// barriers per candidate, warp 0 doing the serial tail). Here a warp owns a signal outright:
+//   * the signal sits in the warp's slice of shared memory; the block is cut into tiles of
+//     32 lanes x R_T samples, a lane keeps its R_T-sample run + MAXORD history in registers;
+//   * a candidate = ntiles x (R_T x NTAPS IMADs per lane), NTAPS chosen per candidate from
+//     {4, 8, 12, 32} so short predictors do not pay for MAXORD taps;
+//   * partition sums land in a heap-indexed tree (node n = 2^po + p); merging partitions is
+//     tree[n] = tree[2n] + tree[2n+1]; every (order, partition) Rice parameter / bit estimate
+//     is evaluated in one sweep over the nodes; orders 0..4 share one 32-lane chunk;
+//   * only __syncwarp() is ever needed.
+// Arithmetic and decision order are identical to k_search / k_search2 (and the reference).
+#pragma once
+
+#include "encode_kernels_v2.cuh"
+
+namespace fb200 {
+
+struct SearchWarpShared {
+	unsigned long long tree[2 * kMaxPartitions];  // heap: node n = (1<<po) + p ; [0] unused
+	uint8_t params_all[2 * kMaxPartitions];       // same indexing
+	uint8_t b_params[kMaxPartitions];
+	uint32_t obits[kMaxPartitionOrder + 1];
+};
+
+template <int R_T, int MAXORD, int NTAPS>
+__device__ __forceinline__ void tile_residual_narrow(const int (&xr)[MAXORD + R_T], const int (&q)[MAXORD], int shift, int (&r)[R_T])
+{
+#pragma unroll
+	for(int m = 0; m < R_T; m++) {
+		int sum = 0;
+#pragma unroll
+		for(int j = 0; j < NTAPS; j++) sum += q[j] * xr[MAXORD + m - 1 - j];
+		r[m] = xr[MAXORD + m] - (sum >> shift);
+	}
+}
+
+template <int R_T, int MAXORD, int NTAPS>
+__device__ __forceinline__ bool tile_residual_wide(const int (&xr)[MAXORD + R_T], const int (&q)[MAXORD], int shift, int (&r)[R_T], int limit)
+{
+	bool bad = false;
+#pragma unroll
+	for(int m = 0; m < R_T; m++) {
+		long long sum = 0;
+#pragma unroll
+		for(int j = 0; j < NTAPS; j++) sum += (long long)q[j] * (long long)xr[MAXORD + m - 1 - j];
+		const long long rr = (long long)xr[MAXORD + m] - (sum >> shift);
+		if(limit && (rr <= (long long)INT32_MIN || rr > (long long)INT32_MAX)) bad = true;
+		r[m] = (int)rr;
+	}
+	return bad;
+}
+
+// |residual| sum of this lane's run for one tile, positions < order masked out.
+template <int R_T, int MAXORD>
+__device__ __forceinline__ unsigned long long tile_abs_sum(const int (&xr)[MAXORD + R_T], const int (&q)[MAXORD], int order, int shift,
+                                                           int wide, int limit, int base, bool narrow_acc, bool &bad)
+{
+	int r[R_T];
+	if(!wide) {
+		if(order <= 4) tile_residual_narrow<R_T, MAXORD, 4>(xr, q, shift, r);
+		else if(MAXORD > 8 && order > 8) {
+			if(MAXORD > 12 && order > 12) tile_residual_narrow<R_T, MAXORD, MAXORD>(xr, q, shift, r);
+			else tile_residual_narrow<R_T, MAXORD, (MAXORD < 12 ? MAXORD : 12)>(xr, q, shift, r);
+		}
+		else tile_residual_narrow<R_T, MAXORD, 8>(xr, q, shift, r);
+	}
+	else {
+		if(MAXORD > 12 && order > 12) bad |= tile_residual_wide<R_T, MAXORD, MAXORD>(xr, q, shift, r, limit);
+		else if(MAXORD > 8 && order > 8) bad |= tile_residual_wide<R_T, MAXORD, (MAXORD < 12 ? MAXORD : 12)>(xr, q, shift, r, limit);
+		else bad |= tile_residual_wide<R_T, MAXORD, 8>(xr, q, shift, r, limit);
+	}
+	if(narrow_acc) {
+		uint32_t s32 = 0;
+#pragma unroll
+		for(int m = 0; m < R_T; m++)
+			if(base + m >= order) s32 += abs_u32(r[m]);
+		return s32;
+	}
+	unsigned long long s = 0;
+#pragma unroll
+	for(int m = 0; m < R_T; m++)
+		if(base + m >= order) s += abs_u32(r[m]);
+	return s;
+}
+
+template <int R_T, int MAXORD, int NW>
+__global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__restrict__ sig, const SigMeta *__restrict__ meta,
+                                                    const CandDesc *__restrict__ cdesc, SubframePlan *__restrict__ plans, int nitems)
+{
+	static_assert(MAXORD >= 8, "tap classes assume MAXORD >= 8");
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, bs = P.bs;
+	const int item = blockIdx.x * NW + warp;
+	if(item >= nitems) return;
+	const int xcap = skew(P.bs_stride) + 1;
+	const size_t per_warp = ((size_t)xcap * 4 + sizeof(SearchWarpShared) + 15) / 16 * 16;
+	int32_t *xs = reinterpret_cast<int32_t *>(smem_raw + per_warp * warp);
+	SearchWarpShared &S = *reinterpret_cast<SearchWarpShared *>(smem_raw + per_warp * warp + (size_t)xcap * 4);
+
+	const SigMeta M = meta[item];
+	SubframePlan *plan = plans + item;
+	if(M.bps == 0) {
+		if(lane == 0) { plan->type = -1; plan->est_bits = 0xffffffffu; }
+		return;
+	}
+	const int sbps = M.bps, wasted = M.wasted;
+	const int32_t *g = sig + (size_t)item * P.bs_stride;
+	for(int i = lane; i < bs; i += 32) xs[skew(i)] = g[i];
+	for(int p = lane; p < kMaxPartitions; p += 32) S.b_params[p] = 0;
+	__syncwarp();
+
+	constexpr int TILE = 32 * R_T;
+	const int ntiles = bs / TILE;
+
+	// best-so-far (uniform across the warp)
+	uint32_t best_bits;
+	int b_type = SF_VERBATIM, b_order = 0, b_prec = 0, b_shift = 0, b_method = 0, b_po = 0, b_wide = 0;
+	int b_q[MAXORD];
+#pragma unroll
+	for(int j = 0; j < MAXORD; j++) b_q[j] = 0;
+	if(P.dis_verb && bs >= (int)kMaxFixedOrder) best_bits = 0xffffffffu;
+	else best_bits = kSubframeHeaderBits + (uint32_t)wasted + (uint32_t)bs * (uint32_t)sbps;
+
+	auto evaluate = [&](int type, int order, int precision, int shift, int wide, int limit, const int (&q)[MAXORD]) {
+		int max_po = P.max_po;
+		while(max_po > 0 && (bs >> max_po) <= order) max_po--;
+		const int min_po = min(P.min_po, max_po);
+		const int psize = bs >> max_po;
+		const bool narrow = (uint32_t)(sbps + (int)kMaxExtraResidualBps) < 32u - ilog2_u32((uint32_t)psize);
+		const int lpp = psize / R_T;  // lanes (runs) per partition at max_po: a power of two
+		const int lpp_log = (int)ilog2_u32((uint32_t)lpp);
+		const int nbase = 1 << max_po;
+		for(int n = nbase + lane; n < 2 * nbase; n += 32) S.tree[n] = 0;
+		__syncwarp();
+		bool bad = false;
+		for(int t = 0; t < ntiles; t++) {
+			const int base = t * TILE + lane * R_T;
+			int xr[MAXORD + R_T];
+#pragma unroll
+			for(int hh = 0; hh < MAXORD; hh++) {
+				const int idx = base - MAXORD + hh;
+				xr[hh] = idx >= 0 ? xs[skew(idx)] : 0;
+			}
+#pragma unroll
+			for(int m = 0; m < R_T; m++) xr[MAXORD + m] = xs[skew(base + m)];
+			unsigned long long s = tile_abs_sum<R_T, MAXORD>(xr, q, order, shift, wide, limit, base, narrow, bad);
+			if(lpp_log <= 5) {
+				for(int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+				if((lane & (lpp - 1)) == 0) S.tree[nbase + ((t * 32 + lane) >> lpp_log)] += s;
+			}
+			else {
+				s = warp_sum_u64(s);
+				if(lane == 0) S.tree[nbase + ((t * 32) >> lpp_log)] += s;
+			}
+			__syncwarp();
+		}
+		if(__any_sync(0xffffffffu, bad)) return;  // evaluate_lpc_subframe_ returns 0 (stream_encoder.c:4601-4609)
+		if(narrow) {
+			for(int n = nbase + lane; n < 2 * nbase; n += 32) S.tree[n] = (unsigned long long)(uint32_t)S.tree[n];
+			__syncwarp();
+		}
+		// merge partitions for the lower orders (precompute_partition_info_sums_, :4837-4851)
+		for(int po = max_po - 1; po >= min_po; po--) {
+			for(int n = (1 << po) + lane; n < (2 << po); n += 32) S.tree[n] = S.tree[2 * n] + S.tree[2 * n + 1];
+			__syncwarp();
+		}
+		// Rice parameter + bit estimate of every (order, partition) node (set_partitioned_rice_, :4954-5075)
+		const int n_lo = 1 << min_po, n_hi = 2 << max_po;
+		for(int c = n_lo >> 5; c * 32 < n_hi; c++) {
+			const int n = c * 32 + lane;
+			const bool valid = n >= n_lo && n < n_hi;
+			unsigned long long bits = 0;
+			int po = 0;
+			if(valid) {
+				po = (int)ilog2_u32((uint32_t)n);
+				const int p = n - (1 << po);
+				const uint32_t pbase = (uint32_t)(bs >> po);
+				uint32_t psamp = pbase, div = 0x40000u / pbase;
+				if(p == 0) { psamp -= (uint32_t)order; div = 0x40000u / psamp; }
+				const unsigned long long mean = S.tree[n];
+				uint32_t k;
+				if(mean < 2 || (((mean - 1) * div) >> 18) == 0) k = 0;
+				else k = ilog2_u64(((mean - 1) * div) >> 18) + 1;
+				if(k >= (uint32_t)P.rice_limit) k = (uint32_t)P.rice_limit - 1;
+				S.params_all[n] = (uint8_t)k;
+				bits = count_rice_bits(k, psamp, mean);
+			}
+			if(c == 0) {
+				// orders 0..4 live in lanes [2^po, 2^(po+1)): segmented butterfly inside aligned power-of-two blocks
+				const int seg = lane ? (1 << ilog2_u32((uint32_t)lane)) : 1;
+#pragma unroll
+				for(int o = 1; o < 16; o <<= 1) {
+					const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+					if(o < seg) bits += other;
+				}
+				if(valid && lane == seg) {
+					const unsigned long long total = bits + (kEntropyTypeLen + kRiceOrderLen);
+					S.obits[po] = (uint32_t)(total < 0xffffffffull ? total : 0xffffffffull);
+				}
+			}
+			else {
+				// a whole chunk belongs to one order (>= 5); orders with more than 32 partitions span several chunks
+				const unsigned long long part = warp_sum_u64(bits);
+				const int cpo = (int)ilog2_u32((uint32_t)(c * 32));
+				const bool first = (c * 32) == (1 << cpo);
+				const bool last = ((c + 1) * 32) == (2 << cpo);
+				unsigned long long acc = part;
+				if(!first) acc += S.tree[0];  // tree[0] is unused by the heap: running total of the current order
+				if(lane == 0) {
+					if(last) {
+						const unsigned long long total = acc + (kEntropyTypeLen + kRiceOrderLen);
+						S.obits[cpo] = (uint32_t)(total < 0xffffffffull ? total : 0xffffffffull);
+					}
+					else S.tree[0] = acc;
+				}
+			}
+			__syncwarp();
+		}
+		uint32_t best_r = 0;
+		int best_po = 0;
+		for(int po = max_po; po >= min_po; po--) {
+			const uint32_t bits = S.obits[po];
+			if(best_r == 0 || bits < best_r) { best_r = bits; best_po = po; }
+		}
+		uint32_t estimate = kSubframeHeaderBits + (uint32_t)wasted;
+		if(type == SF_FIXED) estimate += (uint32_t)order * (uint32_t)sbps;
+		else estimate += kQlpPrecisionLen + kQlpShiftLen + (uint32_t)order * (uint32_t)(precision + sbps);
+		if(best_r < 0xffffffffu - estimate) estimate += best_r;
+		else estimate = 0xffffffffu;
+		const bool better = (type == SF_LPC ? estimate > 0 : true) && estimate < best_bits;
+		if(better) {
+			uint32_t any15 = 0;
+			for(int p = lane; p < (1 << best_po); p += 32) {
+				const uint8_t k = S.params_all[(1 << best_po) + p];
+				S.b_params[p] = k;
+				any15 |= (k >= kRiceEscape) ? 1u : 0u;
+			}
+			any15 = warp_or(any15);
+			best_bits = estimate;
+			b_type = type; b_order = order; b_prec = precision; b_shift = shift; b_method = any15 ? 1 : 0; b_po = best_po; b_wide = wide;
+#pragma unroll
+			for(int j = 0; j < MAXORD; j++) b_q[j] = (type == SF_LPC) ? q[j] : 0;
+		}
+		__syncwarp();
+	};
+
+	if(bs > (int)kMaxFixedOrder) {
+		// fixed-predictor scan (fixed.c:222-290) + constant detection over all tiles
+		unsigned long long te[5] = {0, 0, 0, 0, 0};
+		uint32_t eq = 1;
+		const int32_t x0 = xs[0];
+		for(int t = 0; t < ntiles; t++) {
+			const int base = t * TILE + lane * R_T;
+			int xw[4 + R_T];
+#pragma unroll
+			for(int hh = 0; hh < 4; hh++) {
+				const int idx = base - 4 + hh;
+				xw[hh] = idx >= 0 ? xs[skew(idx)] : 0;
+			}
+#pragma unroll
+			for(int m = 0; m < R_T; m++) xw[4 + m] = xs[skew(base + m)];
+#pragma unroll
+			for(int m = 0; m < R_T; m++) {
+				eq &= (xw[4 + m] == x0) ? 1u : 0u;
+				if(base + m >= (int)kMaxFixedOrder) {
+					const long long d0 = xw[4 + m], d1 = xw[3 + m], d2 = xw[2 + m], d3 = xw[1 + m], d4 = xw[m];
+					const long long e1 = d0 - d1, e2 = d0 - 2 * d1 + d2, e3 = d0 - 3 * d1 + 3 * d2 - d3, e4 = d0 - 4 * d1 + 6 * d2 - 4 * d3 + d4;
+					te[0] += (unsigned long long)(d0 < 0 ? -d0 : d0);
+					te[1] += (unsigned long long)(e1 < 0 ? -e1 : e1);
+					te[2] += (unsigned long long)(e2 < 0 ? -e2 : e2);
+					te[3] += (unsigned long long)(e3 < 0 ? -e3 : e3);
+					te[4] += (unsigned long long)(e4 < 0 ? -e4 : e4);
+				}
+			}
+		}
+#pragma unroll
+		for(int k = 0; k < 5; k++) te[k] = warp_sum_u64(te[k]);
+		eq = warp_and(eq);
+		int guess;
+		{
+			const unsigned long long m34 = te[3] < te[4] ? te[3] : te[4], m234 = te[2] < m34 ? te[2] : m34, m1234 = te[1] < m234 ? te[1] : m234;
+			if(te[0] <= m1234) guess = 0;
+			else if(te[1] <= m234) guess = 1;
+			else if(te[2] <= m34) guess = 2;
+			else if(te[3] <= te[4]) guess = 3;
+			else guess = 4;
+		}
+		float rbps[5];
+		{
+			const double n = (double)(uint32_t)(bs - (int)kMaxFixedOrder);
+#pragma unroll
+			for(int k = 0; k < 5; k++)
+				rbps[k] = (float)((te[k] > 0) ? log(M_LN2 * (double)te[k] / n) / M_LN2 : 0.0);
+		}
+		const bool is_constant = !P.dis_const && rbps[1] == 0.0f && eq;
+		if(is_constant) {
+			const uint32_t cbits = kSubframeHeaderBits + (uint32_t)wasted + (uint32_t)sbps;
+			if(cbits < best_bits) { best_bits = cbits; b_type = SF_CONSTANT; }
+		}
+		else {
+			if(!P.dis_fixed || (P.max_order == 0 && best_bits == 0xffffffffu)) {
+				int lo, hi;
+				if(P.exhaustive) { lo = 0; hi = (int)kMaxFixedOrder; }
+				else lo = hi = guess;
+				if(hi >= bs) hi = bs - 1;
+				for(int fo = lo; fo <= hi; fo++) {
+					if(rbps[fo] >= (float)sbps) continue;
+					int q[MAXORD];
+#pragma unroll
+					for(int j = 0; j < MAXORD; j++) q[j] = fixed_tap(fo, j);
+					evaluate(SF_FIXED, fo, 0, 0, 0, 0, q);
+				}
+			}
+			if(P.max_order > 0) {
+				const CandDesc *cd = cdesc + (size_t)item * P.nslots;
+				for(int c = 0; c < P.nslots; c++) {
+					const CandDesc *D = cd + c;
+					if(!D->valid) continue;
+					int q[MAXORD];
+#pragma unroll
+					for(int j = 0; j < MAXORD; j++) q[j] = __ldg(&D->qlp[j]);
+					evaluate(SF_LPC, D->order, D->precision, D->shift, D->wide, D->limit, q);
+				}
+			}
+		}
+	}
+	if(best_bits == 0xffffffffu) {
+		b_type = SF_VERBATIM;
+		best_bits = kSubframeHeaderBits + (uint32_t)wasted + (uint32_t)bs * (uint32_t)sbps;
+	}
+	if(lane == 0) {
+		plan->type = b_type; plan->order = b_order; plan->wasted = wasted; plan->bps = sbps;
+		plan->precision = b_prec; plan->shift = b_shift; plan->method = b_method; plan->porder = b_po;
+		plan->est_bits = best_bits; plan->wide = b_wide;
+#pragma unroll
+		for(int j = 0; j < FB200_MAX_LPC_ORDER; j++) plan->qlp[j] = (j < MAXORD) ? b_q[j < MAXORD ? j : 0] : 0;
+	}
+	for(int p = lane; p < kMaxPartitions; p += 32) plan->params[p] = S.b_params[p];
+}
+
+}  // namespace fb200

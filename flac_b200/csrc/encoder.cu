@@ -14,7 +14,7 @@
 #include <map>
 #include <vector>
 
-#include "encode_kernels_v2.cuh"
+#include "encode_kernels_v3.cuh"
 
 namespace fb200 {
 
@@ -61,6 +61,8 @@ struct Geometry {
 	DevCand *d_cands = nullptr;
 	size_t search_smem = 0, emit_smem = 0;
 	size_t search2_smem = 0, emit2_smem = 0;
+	int fast_search3 = 0;       // 0, or R_T (32/36) of the warp-per-signal kernel
+	size_t search3_smem = 0;
 	int fast_search = 0, fast_emit = 0;  // 0 = general kernels; emit: 256 / 128 = CTA width of the fast kernel
 	int maxord_t = 8;
 };
@@ -95,8 +97,12 @@ struct fb200_encoder {
 	size_t d_out_cap = 0;
 	unsigned long long *d_offsets = nullptr;
 	size_t d_offsets_cap = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+	std::vector<cudaEvent_t> ev_h2d, ev_comp;
+	unsigned long long *h_totals = nullptr;  // pinned
+	size_t h_totals_cap = 0;
 	uint64_t launches = 0;
+	int search_version = 3;  // FB200_SEARCH_KERNEL=1|2|3 selects the search kernel generation (benchmarks/tests)
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
 	bool prof_on = false;
@@ -228,6 +234,16 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		g.fast_search = (bs % 128 == 0 && bs / 128 <= 36 && k.max_po <= 7) ? 1 : 0;
 		if(bs % 256 == 0 && bs / 256 <= 18) g.fast_emit = 256;
 		else if(bs % 128 == 0 && bs / 128 <= 36) g.fast_emit = 128;
+		{
+			const size_t per_warp = ((size_t)xcap * 4 + sizeof(SearchWarpShared) + 15) / 16 * 16;
+			int rt = 0;
+			if(bs % (32 * 32) == 0) rt = 32;
+			else if(bs % (32 * 36) == 0) rt = 36;
+			if(rt && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * per_warp <= 110 * 1024) {
+				g.fast_search3 = rt;
+				g.search3_smem = 2 * per_warp;
+			}
+		}
 		g.search2_smem = (size_t)xcap * 4;
 		g.emit2_smem = (size_t)xcap * 4 + (size_t)k.slot_words * 4;
 	}
@@ -258,6 +274,14 @@ static void launch_search2(const EncK &k, const fb200_encoder *e, const Geometry
 }
 
 template <int MO>
+static void launch_search3(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
+{
+	const int grid = (nitems + 1) / 2;
+	if(g.fast_search3 == 32) k_search3<32, MO, 2><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+	else k_search3<36, MO, 2><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+}
+
+template <int MO>
 static void launch_emit2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nb, cudaStream_t st)
 {
 	if(g.fast_emit == 256) {
@@ -270,6 +294,8 @@ static void launch_emit2(const EncK &k, const fb200_encoder *e, const Geometry &
 template <int MO>
 static void set_smem_attrs(int search_bytes, int emit_bytes)
 {
+	cudaFuncSetAttribute(k_search3<32, MO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	cudaFuncSetAttribute(k_search3<36, MO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 	cudaFuncSetAttribute(k_search2<32, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
 	cudaFuncSetAttribute(k_search2<36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
 	cudaFuncSetAttribute(k_emit2<256, 16, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
@@ -309,7 +335,12 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
-	if(g.fast_search && !e->use_v1) {
+	if(g.fast_search3 && !e->use_v1 && e->search_version >= 3) {
+		if(g.maxord_t == 8) launch_search3<8>(k, e, g, nitems, st);
+		else if(g.maxord_t == 12) launch_search3<12>(k, e, g, nitems, st);
+		else launch_search3<32>(k, e, g, nitems, st);
+	}
+	else if(g.fast_search && !e->use_v1 && e->search_version >= 2) {
 		if(g.maxord_t == 8) launch_search2<8>(k, e, g, nitems, st);
 		else if(g.maxord_t == 12) launch_search2<12>(k, e, g, nitems, st);
 		else launch_search2<32>(k, e, g, nitems, st);
@@ -498,6 +529,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	{
 		const char *env = getenv("FB200_FORCE_GENERAL_KERNELS");
 		e->use_v1 = env && env[0] == '1';
+		const char *sv = getenv("FB200_SEARCH_KERNEL");
+		if(sv && sv[0] >= '1' && sv[0] <= '3') e->search_version = sv[0] - '0';
 	}
 	*out = e;
 	return FB200_OK;
@@ -515,6 +548,12 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	cudaFree(e->d_running); cudaFree(e->d_err);
 	cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_offsets);
 	if(e->stream) cudaStreamDestroy(e->stream);
+	if(e->s_h2d) cudaStreamDestroy(e->s_h2d);
+	if(e->s_d2h) cudaStreamDestroy(e->s_d2h);
+	for(cudaEvent_t ev : e->ev_h2d) cudaEventDestroy(ev);
+	for(cudaEvent_t ev : e->ev_comp) cudaEventDestroy(ev);
+	if(e->h_totals) cudaFreeHost(e->h_totals);
+	prof_resolve(e);
 	delete e;
 }
 
@@ -572,10 +611,17 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, uint32_t first_frame_number,
                       uint8_t *out, size_t out_capacity, uint64_t *frame_offsets, uint32_t *nframes)
 {
+	// Host-buffer path: the batch is cut into chunks; chunk i+1's H2D copy, chunk i's kernels and
+	// chunk i-1's D2H copy run on three streams (truly asynchronous when the caller's buffers are
+	// pinned; pageable buffers still work, the copies then serialise inside the driver).
 	if(!e || (!pcm && samples) || !out || !frame_offsets) return FB200_ERR_INVALID;
 	FB_CUDA(cudaSetDevice(e->device));
 	const uint32_t bs = e->cfg.blocksize, ch = e->cfg.channels;
-	const uint64_t nfr = (samples + bs - 1) / bs;
+	const uint64_t nfull = samples / bs;
+	const uint32_t tail = (uint32_t)(samples % bs);
+	const uint64_t nfr = nfull + (tail ? 1 : 0);
+	if(nframes) *nframes = (uint32_t)nfr;
+	if(nfr == 0) { frame_offsets[0] = 0; return FB200_OK; }
 	const size_t pcm_bytes = (size_t)samples * ch * sizeof(int32_t);
 	const size_t need_out = (size_t)nfr * max_frame_bytes_for(e->cfg, (int)bs) + 64;
 	if(pcm_bytes > e->d_pcm_cap) {
@@ -593,17 +639,61 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 		FB_CUDA(cudaMalloc(&e->d_offsets, (nfr + 1) * sizeof(unsigned long long)));
 		e->d_offsets_cap = nfr + 1;
 	}
-	if(pcm_bytes) FB_CUDA(cudaMemcpyAsync(e->d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, e->stream));
-	uint64_t total = 0;
-	uint32_t nf = 0;
-	const int rc = fb200_encode_device(e, e->d_pcm, samples, first_frame_number, e->d_out, e->d_out_cap,
-	                                   reinterpret_cast<uint64_t *>(e->d_offsets), &nf, &total, e->stream, 1);
-	if(rc != FB200_OK) return rc;
-	if(nframes) *nframes = nf;
-	if(total > out_capacity) { set_error("output buffer too small: need %llu bytes", (unsigned long long)total); return FB200_ERR_OUTPUT_TOO_SMALL; }
-	FB_CUDA(cudaMemcpyAsync(out, e->d_out, total, cudaMemcpyDeviceToHost, e->stream));
-	FB_CUDA(cudaMemcpyAsync(frame_offsets, e->d_offsets, (nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-	FB_CUDA(cudaStreamSynchronize(e->stream));
+	if(!e->s_h2d) FB_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+	if(!e->s_d2h) FB_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+	// chunking: ~5 chunks per call, between 256 blocks and the launch capacity; the short last block is its own chunk
+	uint64_t chunk = (nfull + 4) / 5;
+	if(chunk < 256) chunk = 256;
+	if(chunk > e->max_blocks) chunk = e->max_blocks;
+	struct Chunk { uint64_t first; uint32_t nb; uint32_t blocksize; };
+	std::vector<Chunk> chunks;
+	for(uint64_t done = 0; done < nfull; done += chunk)
+		chunks.push_back(Chunk{done, (uint32_t)((nfull - done) < chunk ? (nfull - done) : chunk), bs});
+	if(tail) chunks.push_back(Chunk{nfull, 1, tail});
+	const size_t used = chunks.size();
+	if(used > e->h_totals_cap) {
+		if(e->h_totals) cudaFreeHost(e->h_totals);
+		e->h_totals = nullptr; e->h_totals_cap = 0;
+		FB_CUDA(cudaMallocHost(&e->h_totals, (used + 16) * sizeof(unsigned long long)));
+		e->h_totals_cap = used + 16;
+	}
+	while(e->ev_h2d.size() < used) {
+		cudaEvent_t ea, eb;
+		FB_CUDA(cudaEventCreateWithFlags(&ea, cudaEventDisableTiming));
+		FB_CUDA(cudaEventCreateWithFlags(&eb, cudaEventDisableTiming));
+		e->ev_h2d.push_back(ea); e->ev_comp.push_back(eb);
+	}
+	cudaStream_t sc = e->stream;
+	FB_CUDA(cudaMemsetAsync(e->d_running, 0, sizeof(unsigned long long), sc));
+	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), sc));
+	for(size_t ci = 0; ci < used; ci++) {
+		const Chunk &c = chunks[ci];
+		const size_t off_elems = (size_t)c.first * bs * ch;
+		const size_t nsamp = (size_t)c.nb * c.blocksize;
+		Geometry *g = nullptr;
+		int rc;
+		FB_CUDA(cudaMemcpyAsync(e->d_pcm + off_elems, pcm + off_elems, nsamp * ch * sizeof(int32_t), cudaMemcpyHostToDevice, e->s_h2d));
+		FB_CUDA(cudaEventRecord(e->ev_h2d[ci], e->s_h2d));
+		FB_CUDA(cudaStreamWaitEvent(sc, e->ev_h2d[ci], 0));
+		if((rc = build_geometry(e, (int)c.blocksize, &g)) != FB200_OK) return rc;
+		if((rc = run_blocks(e, *g, e->d_pcm + off_elems, (int)c.nb, first_frame_number + (uint32_t)c.first, c.first, e->d_out, e->d_out_cap, e->d_offsets, sc)) != FB200_OK) return rc;
+		FB_CUDA(cudaMemcpyAsync(&e->h_totals[ci], e->d_running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
+		FB_CUDA(cudaEventRecord(e->ev_comp[ci], sc));
+	}
+	unsigned long long prev = 0;
+	for(size_t i = 0; i < used; i++) {
+		FB_CUDA(cudaEventSynchronize(e->ev_comp[i]));
+		const unsigned long long tot = e->h_totals[i];
+		if(tot > out_capacity) { cudaStreamSynchronize(sc); set_error("output buffer too small: need more than %llu bytes", tot); return FB200_ERR_OUTPUT_TOO_SMALL; }
+		if(tot > prev) FB_CUDA(cudaMemcpyAsync(out + prev, e->d_out + prev, (size_t)(tot - prev), cudaMemcpyDeviceToHost, e->s_d2h));
+		prev = tot;
+	}
+	FB_CUDA(cudaMemcpyAsync(frame_offsets, e->d_offsets, (nfr + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->s_d2h));
+	FB_CUDA(cudaStreamSynchronize(e->s_d2h));
+	FB_CUDA(cudaStreamSynchronize(sc));
+	int err = 0;
+	FB_CUDA(cudaMemcpy(&err, e->d_err, sizeof err, cudaMemcpyDeviceToHost));
+	if(err) { set_error("internal output buffer too small"); return FB200_ERR_OUTPUT_TOO_SMALL; }
 	return FB200_OK;
 }
 
