@@ -95,9 +95,10 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 	const int item = blockIdx.x * NW + warp;
 	if(item >= nitems) return;
 	const int xcap = skew(P.bs_stride) + 1;
-	const size_t per_warp = ((size_t)xcap * 4 + sizeof(SearchWarpShared) + 15) / 16 * 16;
+	const size_t xs_bytes = ((size_t)xcap * 4 + 15) / 16 * 16;
+	const size_t per_warp = xs_bytes + (sizeof(SearchWarpShared) + 15) / 16 * 16;
 	int32_t *xs = reinterpret_cast<int32_t *>(smem_raw + per_warp * warp);
-	SearchWarpShared &S = *reinterpret_cast<SearchWarpShared *>(smem_raw + per_warp * warp + (size_t)xcap * 4);
+	SearchWarpShared &S = *reinterpret_cast<SearchWarpShared *>(smem_raw + per_warp * warp + xs_bytes);
 
 	const SigMeta M = meta[item];
 	SubframePlan *plan = plans + item;

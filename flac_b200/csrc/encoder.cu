@@ -235,7 +235,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		if(bs % 256 == 0 && bs / 256 <= 18) g.fast_emit = 256;
 		else if(bs % 128 == 0 && bs / 128 <= 36) g.fast_emit = 128;
 		{
-			const size_t per_warp = ((size_t)xcap * 4 + sizeof(SearchWarpShared) + 15) / 16 * 16;
+			const size_t per_warp = ((size_t)xcap * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared) + 15) / 16 * 16;
 			int rt = 0;
 			if(bs % (32 * 32) == 0) rt = 32;
 			else if(bs % (32 * 36) == 0) rt = 36;
