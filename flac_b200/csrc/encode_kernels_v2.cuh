@@ -12,15 +12,22 @@ namespace fb200 {
 // Same chain-per-thread scheme as k_autoc, but every thread fetches its samples with aligned
 // 128-bit loads (one L1 wavefront per lane per 4 samples instead of per sample) in bodies of
 // U = lcm(LAGS,4) samples, so the rotating-history indices stay compile-time.
-template <int LAGS, int U>
+// SPLIT threads share one chain: thread `part` owns lags [part*NACC, part*NACC+NACC) and therefore needs a
+// history of HIST = SPLIT*NACC samples. Every partial chain still adds its terms in ascending sample order,
+// so the result is bit-identical to the unsplit kernel; the split only buys parallelism (the kernel is
+// latency-bound: ncu shows the FP64 pipe ~1/3 busy).
+template <int NACC, int SPLIT, int U>
 __global__ void __launch_bounds__(128) k_autoc2(EncK P, const int32_t *__restrict__ sig, const SigMeta *__restrict__ meta,
                                                const float *__restrict__ windows, const DevSection *__restrict__ secs,
                                                double *__restrict__ autoc, int nitems)
 {
-	static_assert(U % LAGS == 0 && U % 4 == 0, "U must be a common multiple of LAGS and 4");
+	constexpr int HIST = NACC * SPLIT;
+	static_assert(U % HIST == 0 && U % 4 == 0, "U must be a common multiple of the history depth and 4");
 	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-	if(gid >= nitems * P.nsec) return;
-	const int sec = gid / nitems, item = gid - sec * nitems;
+	if(gid >= nitems * P.nsec * SPLIT) return;
+	const int part = gid / (nitems * P.nsec);
+	const int rem = gid - part * (nitems * P.nsec);
+	const int sec = rem / nitems, item = rem - sec * nitems;
 	if(meta[item].bps == 0) return;
 	const DevSection S = secs[sec];
 	const int32_t *x = sig + (size_t)item * P.bs_stride;
@@ -30,15 +37,22 @@ __global__ void __launch_bounds__(128) k_autoc2(EncK P, const int32_t *__restric
 	const int nvalid = S.partial ? 2 * S.part_size : S.data_len;  // d[i] == 0 beyond (lpc.c:90-91)
 	const int span = shift - a0 + S.data_len;
 	const int wsecond = P.bs - 2 * S.part_size;     // window index offset of the falling half
+	const int l0 = part * NACC;
 
-	double acc[LAGS], h[LAGS];
+	double acc[NACC], h[HIST];
 #pragma unroll
-	for(int l = 0; l < LAGS; l++) { acc[l] = 0.0; h[l] = 0.0; }
+	for(int l = 0; l < NACC; l++) acc[l] = 0.0;
+#pragma unroll
+	for(int l = 0; l < HIST; l++) h[l] = 0.0;
 
+	int4 v[U / 4];
+#pragma unroll
+	for(int q = 0; q < U / 4; q++) v[q] = __ldg(reinterpret_cast<const int4 *>(x + a0) + q);
 	for(int base = 0; base < span; base += U) {
-		int4 v[U / 4];
+		// software prefetch of the next body (the sig allocation has slack past the last block)
+		int4 vn[U / 4];
 #pragma unroll
-		for(int q = 0; q < U / 4; q++) v[q] = __ldg(reinterpret_cast<const int4 *>(x + a0 + base) + q);
+		for(int q = 0; q < U / 4; q++) vn[q] = __ldg(reinterpret_cast<const int4 *>(x + a0 + base + U) + q);
 #pragma unroll
 		for(int u = 0; u < U; u++) {
 			const int i = a0 + base + u - shift;  // index inside the section
@@ -49,15 +63,28 @@ __global__ void __launch_bounds__(128) k_autoc2(EncK P, const int32_t *__restric
 				d = __fmul_rn((float)xv, __ldg(w + wi));
 			}
 			const double dv = (double)d;
-			const int su = (LAGS - (u % LAGS)) % LAGS;
+			const int su = (HIST - (u % HIST)) % HIST;  // slot of the newest sample; slot (su+l)%HIST holds d[i-l]
 			h[su] = dv;
+			if(SPLIT == 1) {
 #pragma unroll
-			for(int l = 0; l < LAGS; l++) acc[l] = fma(dv, h[(su + l) % LAGS], acc[l]);
+				for(int l = 0; l < NACC; l++) acc[l] = fma(dv, h[(su + l) % HIST], acc[l]);
+			}
+			else if(part == 0) {
+#pragma unroll
+				for(int l = 0; l < NACC; l++) acc[l] = fma(dv, h[(su + l) % HIST], acc[l]);
+			}
+			else {
+#pragma unroll
+				for(int l = 0; l < NACC; l++) acc[l] = fma(dv, h[(su + NACC + l) % HIST], acc[l]);
+			}
 		}
+#pragma unroll
+		for(int q = 0; q < U / 4; q++) v[q] = vn[q];
 	}
 	double *out = autoc + ((size_t)sec * nitems + item) * P.lag_stride;
 #pragma unroll
-	for(int l = 0; l < LAGS; l++) out[l] = acc[l];
+	for(int l = 0; l < NACC; l++)
+		if(l0 + l < P.lag_stride) out[l0 + l] = acc[l];
 }
 
 // ================================================================ register-window residual

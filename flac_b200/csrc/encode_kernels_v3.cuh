@@ -24,78 +24,65 @@ struct SearchWarpShared {
 	uint32_t obits[kMaxPartitionOrder + 1];
 };
 
-template <int R_T, int MAXORD, int NTAPS>
-__device__ __forceinline__ void tile_residual_narrow(const int (&xr)[MAXORD + R_T], const int (&q)[MAXORD], int shift, int (&r)[R_T])
+// Row layout of a warp's signal slice: sample i lives at word (i / R_T) * 36 + (i % R_T). A row is one
+// lane's run; the 36-word row stride makes every 128-bit load of a quarter warp hit 8 distinct
+// bank groups (R_T = 36: identity layout; R_T = 32: 4 pad words per row).
+template <int R_T>
+__device__ __forceinline__ int row_word(int i)
 {
-#pragma unroll
-	for(int m = 0; m < R_T; m++) {
-		int sum = 0;
-#pragma unroll
-		for(int j = 0; j < NTAPS; j++) sum += q[j] * xr[MAXORD + m - 1 - j];
-		r[m] = xr[MAXORD + m] - (sum >> shift);
-	}
+	return R_T == 32 ? i + 4 * (i >> 5) : i;
 }
 
-template <int R_T, int MAXORD, int NTAPS>
-__device__ __forceinline__ bool tile_residual_wide(const int (&xr)[MAXORD + R_T], const int (&q)[MAXORD], int shift, int (&r)[R_T], int limit)
+// |residual| sum of G consecutive outputs. xg[MAXORD + m] = output sample m, xg[0..MAXORD) = history.
+// MASKED: leave out the first ord0 outputs (the warm-up samples of the block's very first group;
+// order <= MAXORD <= ... so only outputs m < MAXORD can be masked).
+// The body is deliberately small (G x NTAPS MACs): the callers loop over groups with a ROLLED loop so
+// the hot code stays inside the instruction cache (a fully unrolled 32 x 12 run per variant did not:
+// ncu showed 30 % "no_instructions" stalls).
+template <int G, int MAXORD, int NTAPS, bool WIDE, bool MASKED, bool NARROW>
+__device__ __forceinline__ void group_abs_sum(const int (&xg)[MAXORD + G], const int (&q)[MAXORD], int shift, int ord0, int limit,
+                                              uint32_t &s32, unsigned long long &s64, bool &bad)
 {
-	bool bad = false;
+	constexpr bool narrow_acc = NARROW;
 #pragma unroll
-	for(int m = 0; m < R_T; m++) {
-		long long sum = 0;
+	for(int m = 0; m < G; m++) {
+		uint32_t a;
+		bool keep = true;
+		if(MASKED && m < MAXORD) keep = m >= ord0;
+		if(!WIDE) {
+			int sum = 0;
 #pragma unroll
-		for(int j = 0; j < NTAPS; j++) sum += (long long)q[j] * (long long)xr[MAXORD + m - 1 - j];
-		const long long rr = (long long)xr[MAXORD + m] - (sum >> shift);
-		if(limit && (rr <= (long long)INT32_MIN || rr > (long long)INT32_MAX)) bad = true;
-		r[m] = (int)rr;
-	}
-	return bad;
-}
-
-// |residual| sum of this lane's run for one tile, positions < order masked out.
-template <int R_T, int MAXORD>
-__device__ __forceinline__ unsigned long long tile_abs_sum(const int (&xr)[MAXORD + R_T], const int (&q)[MAXORD], int order, int shift,
-                                                           int wide, int limit, int base, bool narrow_acc, bool &bad)
-{
-	int r[R_T];
-	if(!wide) {
-		if(order <= 4) tile_residual_narrow<R_T, MAXORD, 4>(xr, q, shift, r);
-		else if(MAXORD > 8 && order > 8) {
-			if(MAXORD > 12 && order > 12) tile_residual_narrow<R_T, MAXORD, MAXORD>(xr, q, shift, r);
-			else tile_residual_narrow<R_T, MAXORD, (MAXORD < 12 ? MAXORD : 12)>(xr, q, shift, r);
+			for(int j = 0; j < NTAPS; j++) sum += q[j] * xg[MAXORD + m - 1 - j];
+			const int pred = sum >> shift;
+			if(narrow_acc && !(MASKED && m < MAXORD)) { s32 = __sad(xg[MAXORD + m], pred, s32); continue; }
+			a = __sad(xg[MAXORD + m], pred, 0u);
 		}
-		else tile_residual_narrow<R_T, MAXORD, 8>(xr, q, shift, r);
-	}
-	else {
-		if(MAXORD > 12 && order > 12) bad |= tile_residual_wide<R_T, MAXORD, MAXORD>(xr, q, shift, r, limit);
-		else if(MAXORD > 8 && order > 8) bad |= tile_residual_wide<R_T, MAXORD, (MAXORD < 12 ? MAXORD : 12)>(xr, q, shift, r, limit);
-		else bad |= tile_residual_wide<R_T, MAXORD, 8>(xr, q, shift, r, limit);
-	}
-	if(narrow_acc) {
-		uint32_t s32 = 0;
+		else {
+			long long sum = 0;
 #pragma unroll
-		for(int m = 0; m < R_T; m++)
-			if(base + m >= order) s32 += abs_u32(r[m]);
-		return s32;
+			for(int j = 0; j < NTAPS; j++) sum += (long long)q[j] * (long long)xg[MAXORD + m - 1 - j];
+			const long long rr = (long long)xg[MAXORD + m] - (sum >> shift);
+			if(limit && (rr <= (long long)INT32_MIN || rr > (long long)INT32_MAX)) bad = true;  // lpc.c:868-884
+			a = abs_u32((int)rr);
+		}
+		if(keep) { if(narrow_acc) s32 += a; else s64 += a; }
 	}
-	unsigned long long s = 0;
-#pragma unroll
-	for(int m = 0; m < R_T; m++)
-		if(base + m >= order) s += abs_u32(r[m]);
-	return s;
 }
 
-template <int R_T, int MAXORD, int NW>
+// WIDEK: the stream needs 64-bit FIR accumulation (bits_per_sample > 16). For <= 16-bit streams the
+// reference's precision clamp (stream_encoder.c:4591-4595) guarantees 32-bit sums, so the narrow kernel
+// only keeps a compact wide fallback for the (never observed) `limit` case.
+template <int R_T, int MAXORD, int NW, bool WIDEK>
 __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__restrict__ sig, const SigMeta *__restrict__ meta,
                                                     const CandDesc *__restrict__ cdesc, SubframePlan *__restrict__ plans, int nitems)
 {
-	static_assert(MAXORD >= 8, "tap classes assume MAXORD >= 8");
+	static_assert(MAXORD >= 8 && MAXORD % 4 == 0 && R_T % 4 == 0, "vector loads need multiples of 4");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, bs = P.bs;
 	const int item = blockIdx.x * NW + warp;
 	if(item >= nitems) return;
-	const int xcap = skew(P.bs_stride) + 1;
-	const size_t xs_bytes = ((size_t)xcap * 4 + 15) / 16 * 16;
+	const int nrows = bs / R_T;
+	const size_t xs_bytes = ((size_t)nrows * 36 * 4 + 15) / 16 * 16;
 	const size_t per_warp = xs_bytes + (sizeof(SearchWarpShared) + 15) / 16 * 16;
 	int32_t *xs = reinterpret_cast<int32_t *>(smem_raw + per_warp * warp);
 	SearchWarpShared &S = *reinterpret_cast<SearchWarpShared *>(smem_raw + per_warp * warp + xs_bytes);
@@ -108,12 +95,27 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 	}
 	const int sbps = M.bps, wasted = M.wasted;
 	const int32_t *g = sig + (size_t)item * P.bs_stride;
-	for(int i = lane; i < bs; i += 32) xs[skew(i)] = g[i];
+	for(int i = lane; i < bs; i += 32) xs[row_word<R_T>(i)] = g[i];
 	for(int p = lane; p < kMaxPartitions; p += 32) S.b_params[p] = 0;
 	__syncwarp();
 
 	constexpr int TILE = 32 * R_T;
+	constexpr int GAPV = (R_T == 32 ? 4 : 0) / 4;  // pad int4s between a row's history and its start
 	const int ntiles = bs / TILE;
+
+	constexpr int G = (R_T == 32) ? 16 : 12;   // outputs per group
+	constexpr int NG = R_T / G;                // groups per run
+	// loads group `g` of row `row` (+ MAXORD history samples) with 128-bit shared loads
+	auto load_group = [&](int row, int g, int (&xg)[MAXORD + G]) {
+		const int sv0 = (row * R_T + g * G) / 4 - MAXORD / 4;  // first sample-vector (4 samples) needed
+#pragma unroll
+		for(int k = 0; k < (MAXORD + G) / 4; k++) {
+			const int sv = sv0 + k;
+			int4 v = make_int4(0, 0, 0, 0);
+			if(sv >= 0) v = *reinterpret_cast<const int4 *>(xs + (R_T == 32 ? 4 * sv + 4 * (sv >> 3) : 4 * sv));
+			xg[4 * k] = v.x; xg[4 * k + 1] = v.y; xg[4 * k + 2] = v.z; xg[4 * k + 3] = v.w;
+		}
+	};
 
 	// best-so-far (uniform across the warp)
 	uint32_t best_bits;
@@ -136,17 +138,48 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 		for(int n = nbase + lane; n < 2 * nbase; n += 32) S.tree[n] = 0;
 		__syncwarp();
 		bool bad = false;
-		for(int t = 0; t < ntiles; t++) {
-			const int base = t * TILE + lane * R_T;
-			int xr[MAXORD + R_T];
-#pragma unroll
-			for(int hh = 0; hh < MAXORD; hh++) {
-				const int idx = base - MAXORD + hh;
-				xr[hh] = idx >= 0 ? xs[skew(idx)] : 0;
-			}
-#pragma unroll
-			for(int m = 0; m < R_T; m++) xr[MAXORD + m] = xs[skew(base + m)];
-			unsigned long long s = tile_abs_sum<R_T, MAXORD>(xr, q, order, shift, wide, limit, base, narrow, bad);
+		// tap class of this candidate: the rolled group loop below runs one small body per class
+		const int cls = wide ? (WIDEK ? ((MAXORD > 12 && order > 12) ? 5 : (MAXORD > 8 && order > 8) ? 4 : 3) : 6)
+		                     : ((MAXORD > 12 && order > 12) ? 2 : (MAXORD > 8 && order > 8) ? 1 : 0);
+		constexpr int NT12 = MAXORD < 12 ? MAXORD : 12;
+		uint32_t s32 = 0;
+		unsigned long long s64 = 0;
+#define FB200_RUN_GROUP(MK, ORD0)                                                                                            \
+	do {                                                                                                                   \
+		if(narrow) {                                                                                                       \
+			switch(cls) {                                                                                                  \
+				case 0: group_abs_sum<G, MAXORD, 8, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;         \
+				case 1: group_abs_sum<G, MAXORD, NT12, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;      \
+				case 2: group_abs_sum<G, MAXORD, MAXORD, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;    \
+				case 3: group_abs_sum<G, MAXORD, 8, true, MK, true>(xg, q, shift, ORD0, limit, s32, s64, bad); break;      \
+				case 4: group_abs_sum<G, MAXORD, NT12, true, MK, true>(xg, q, shift, ORD0, limit, s32, s64, bad); break;   \
+				default: group_abs_sum<G, MAXORD, MAXORD, true, MK, true>(xg, q, shift, ORD0, limit, s32, s64, bad); break; \
+			}                                                                                                              \
+		}                                                                                                                  \
+		else {                                                                                                             \
+			switch(cls) {                                                                                                  \
+				case 0: group_abs_sum<G, MAXORD, 8, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;        \
+				case 1: group_abs_sum<G, MAXORD, NT12, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;     \
+				case 2: group_abs_sum<G, MAXORD, MAXORD, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;   \
+				case 3: group_abs_sum<G, MAXORD, 8, true, MK, false>(xg, q, shift, ORD0, limit, s32, s64, bad); break;     \
+				case 4: group_abs_sum<G, MAXORD, NT12, true, MK, false>(xg, q, shift, ORD0, limit, s32, s64, bad); break;  \
+				default: group_abs_sum<G, MAXORD, MAXORD, true, MK, false>(xg, q, shift, ORD0, limit, s32, s64, bad); break; \
+			}                                                                                                              \
+		}                                                                                                                  \
+	} while(0)
+		{   // group 0 of row 0 carries the warm-up mask (only lane 0 has ord0 != 0)
+			int xg[MAXORD + G];
+			load_group(lane, 0, xg);
+			const int ord0 = lane == 0 ? order : 0;
+			FB200_RUN_GROUP(true, ord0);
+		}
+#pragma unroll 1
+		for(int gi = 1; gi <= ntiles * NG; gi++) {
+			const int t = (gi - 1) / NG, gdone = (gi - 1) % NG;  // group (t, gdone) has just been accumulated
+			if(gdone == NG - 1) {
+				// a run is complete: fold it into its partition
+				unsigned long long s = narrow ? (unsigned long long)s32 : s64;
+				s32 = 0; s64 = 0;
 			if(lpp_log <= 5) {
 				for(int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
 				if((lane & (lpp - 1)) == 0) S.tree[nbase + ((t * 32 + lane) >> lpp_log)] += s;
@@ -156,6 +189,18 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 				if(lane == 0) S.tree[nbase + ((t * 32) >> lpp_log)] += s;
 			}
 			__syncwarp();
+			}
+			if(gi == ntiles * NG) break;
+			{
+				int xg[MAXORD + G];
+				load_group((gi / NG) * 32 + lane, gi % NG, xg);
+				if(MAXORD > G && gi < NG) {
+					// the warm-up region (order <= MAXORD samples) reaches past the first group of the block's first run
+					const int ord_g = (lane == 0 && order > gi * G) ? order - gi * G : 0;
+					FB200_RUN_GROUP(true, ord_g);
+				}
+				else FB200_RUN_GROUP(false, 0);
+			}
 		}
 		if(__any_sync(0xffffffffu, bad)) return;  // evaluate_lpc_subframe_ returns 0 (stream_encoder.c:4601-4609)
 		if(narrow) {
@@ -253,15 +298,19 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 		uint32_t eq = 1;
 		const int32_t x0 = xs[0];
 		for(int t = 0; t < ntiles; t++) {
-			const int base = t * TILE + lane * R_T;
+			const int row = t * 32 + lane;
+			const int base = row * R_T;
 			int xw[4 + R_T];
+			{
+				const int4 *pv = reinterpret_cast<const int4 *>(xs + row * 36);
+				if(row == 0) { xw[0] = xw[1] = xw[2] = xw[3] = 0; }
+				else { const int4 v = pv[-1 - GAPV]; xw[0] = v.x; xw[1] = v.y; xw[2] = v.z; xw[3] = v.w; }
 #pragma unroll
-			for(int hh = 0; hh < 4; hh++) {
-				const int idx = base - 4 + hh;
-				xw[hh] = idx >= 0 ? xs[skew(idx)] : 0;
+				for(int k = 0; k < R_T / 4; k++) {
+					const int4 v = pv[k];
+					xw[4 + 4 * k] = v.x; xw[5 + 4 * k] = v.y; xw[6 + 4 * k] = v.z; xw[7 + 4 * k] = v.w;
+				}
 			}
-#pragma unroll
-			for(int m = 0; m < R_T; m++) xw[4 + m] = xs[skew(base + m)];
 #pragma unroll
 			for(int m = 0; m < R_T; m++) {
 				eq &= (xw[4 + m] == x0) ? 1u : 0u;

@@ -102,6 +102,7 @@ struct fb200_encoder {
 	unsigned long long *h_totals = nullptr;  // pinned
 	size_t h_totals_cap = 0;
 	uint64_t launches = 0;
+	bool autoc_split = false;
 	int search_version = 3;  // FB200_SEARCH_KERNEL=1|2|3 selects the search kernel generation (benchmarks/tests)
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
@@ -235,10 +236,10 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		if(bs % 256 == 0 && bs / 256 <= 18) g.fast_emit = 256;
 		else if(bs % 128 == 0 && bs / 128 <= 36) g.fast_emit = 128;
 		{
-			const size_t per_warp = ((size_t)xcap * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared) + 15) / 16 * 16;
 			int rt = 0;
 			if(bs % (32 * 32) == 0) rt = 32;
 			else if(bs % (32 * 36) == 0) rt = 36;
+			const size_t per_warp = rt ? (((size_t)(bs / rt) * 36 * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared) + 15) / 16 * 16) : 0;
 			if(rt && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * per_warp <= 110 * 1024) {
 				g.fast_search3 = rt;
 				g.search3_smem = 2 * per_warp;
@@ -259,11 +260,11 @@ static void launch_autoc(const EncK &k, const fb200_encoder *e, const Geometry &
 	k_autoc<LAGS><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
 }
 
-template <int LAGS, int U>
+template <int NACC, int SPLIT, int U>
 static void launch_autoc2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
 {
-	const int total = nitems * k.nsec;
-	k_autoc2<LAGS, U><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
+	const int total = nitems * k.nsec * SPLIT;
+	k_autoc2<NACC, SPLIT, U><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
 }
 
 template <int MO>
@@ -277,8 +278,15 @@ template <int MO>
 static void launch_search3(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
 {
 	const int grid = (nitems + 1) / 2;
-	if(g.fast_search3 == 32) k_search3<32, MO, 2><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-	else k_search3<36, MO, 2><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+	const bool widek = k.bps > 16;
+	if(g.fast_search3 == 32) {
+		if(widek) k_search3<32, MO, 2, true><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+		else k_search3<32, MO, 2, false><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+	}
+	else {
+		if(widek) k_search3<36, MO, 2, true><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+		else k_search3<36, MO, 2, false><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+	}
 }
 
 template <int MO>
@@ -294,8 +302,10 @@ static void launch_emit2(const EncK &k, const fb200_encoder *e, const Geometry &
 template <int MO>
 static void set_smem_attrs(int search_bytes, int emit_bytes)
 {
-	cudaFuncSetAttribute(k_search3<32, MO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search3<36, MO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	cudaFuncSetAttribute(k_search3<32, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	cudaFuncSetAttribute(k_search3<36, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	cudaFuncSetAttribute(k_search3<32, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	cudaFuncSetAttribute(k_search3<36, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 	cudaFuncSetAttribute(k_search2<32, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
 	cudaFuncSetAttribute(k_search2<36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
 	cudaFuncSetAttribute(k_emit2<256, 16, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
@@ -323,11 +333,22 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 			else launch_autoc<33>(k, e, g, nitems, st);
 		}
 		else {
-			if(k.lags <= 7) launch_autoc2<7, 28>(k, e, g, nitems, st);
-			else if(k.lags <= 9) launch_autoc2<9, 36>(k, e, g, nitems, st);
-			else if(k.lags <= 13) launch_autoc2<13, 52>(k, e, g, nitems, st);
-			else if(k.lags <= 17) launch_autoc2<17, 68>(k, e, g, nitems, st);
-			else launch_autoc2<33, 132>(k, e, g, nitems, st);
+			// one thread per chain (splitting the lags over two threads was measured slower: the sample
+			// stream conversion is paid twice); FB200_AUTOC_SPLIT=1 keeps the split variant selectable
+			if(e->autoc_split) {
+				if(k.lags <= 7) launch_autoc2<4, 2, 8>(k, e, g, nitems, st);
+				else if(k.lags <= 9) launch_autoc2<5, 2, 20>(k, e, g, nitems, st);
+				else if(k.lags <= 13) launch_autoc2<7, 2, 28>(k, e, g, nitems, st);
+				else if(k.lags <= 17) launch_autoc2<9, 2, 36>(k, e, g, nitems, st);
+				else launch_autoc2<17, 2, 68>(k, e, g, nitems, st);
+			}
+			else {
+				if(k.lags <= 7) launch_autoc2<7, 1, 28>(k, e, g, nitems, st);
+				else if(k.lags <= 9) launch_autoc2<9, 1, 36>(k, e, g, nitems, st);
+				else if(k.lags <= 13) launch_autoc2<13, 1, 52>(k, e, g, nitems, st);
+				else if(k.lags <= 17) launch_autoc2<17, 1, 68>(k, e, g, nitems, st);
+				else launch_autoc2<33, 1, 132>(k, e, g, nitems, st);
+			}
 		}
 		prof_mark(e, FB200_PROF_AUTOC, st);
 		const int total = nitems * k.nwin;
@@ -529,6 +550,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	{
 		const char *env = getenv("FB200_FORCE_GENERAL_KERNELS");
 		e->use_v1 = env && env[0] == '1';
+		const char *as = getenv("FB200_AUTOC_SPLIT");
+		e->autoc_split = as && as[0] == '1';
 		const char *sv = getenv("FB200_SEARCH_KERNEL");
 		if(sv && sv[0] >= '1' && sv[0] <= '3') e->search_version = sv[0] - '0';
 	}
