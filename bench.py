@@ -122,6 +122,52 @@ def ncu_traffic():
     return {}
 
 
+class Ranks:
+    """One process per GPU; the path shards by block ranges with no data-path collective, so the only
+    collectives are the barrier and the MAX/SUM reductions of timings and unit counts."""
+
+    def __init__(self, backend=None, device=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dist = None
+        self.device = device
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.dist = dist
+            if backend == "nccl":
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group(backend or "gloo")
+
+    def shard_seed(self, base=1):
+        """Every rank encodes its own block range ("file"): distinct, deterministic input per rank."""
+        return base + self.rank
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _reduce(self, v, op):
+        if self.dist is None:
+            return float(v)
+        import torch
+        t = torch.tensor([float(v)], dtype=torch.float64, device=self.device or "cpu")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, v):
+        return self._reduce(v, self.dist.ReduceOp.MAX if self.dist else None)
+
+    def sum(self, v):
+        return self._reduce(v, self.dist.ReduceOp.SUM if self.dist else None)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
 def host_threads():
     return max(1, min(os.cpu_count() or 1, 64))  # FLAC__STREAM_ENCODER_MAX_THREADS = 64
 
@@ -345,29 +391,9 @@ def main():
         print(json.dumps({"error": "no CUDA device: flac_b200 has no CPU fallback"}))
         return 2
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    ranks = Ranks(backend="nccl", device="cuda")
+    dist = ranks.dist
+    barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     if args.workload == "cfg5":
         return bench_decode(args, rank, local_rank, world, dist, barrier, max_over_ranks, sum_over_ranks, config)

@@ -90,6 +90,12 @@ struct fb200_encoder {
 	unsigned long long *d_running = nullptr;
 	int *d_err = nullptr;
 	size_t max_nsec = 0, max_nslots = 0, lag_stride = 0;
+	// stage-A outputs are double-buffered so that stage A (prep/autoc/lpc) of sub-batch i+1 can run on
+	// s_a concurrently with stage B (search/emit/scan/gather) of sub-batch i on the caller's stream
+	struct WS { int32_t *d_sig; SigMeta *d_meta; int *d_blkflags; double *d_autoc; CandDesc *d_cdesc; } ws[2] = {};
+	cudaStream_t s_a = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+	bool ev_b_valid[2] = {false, false};
 	// staging for the host entry point
 	int32_t *d_pcm = nullptr;
 	size_t d_pcm_cap = 0;
@@ -313,12 +319,16 @@ static void set_smem_attrs(int search_bytes, int emit_bytes)
 	cudaFuncSetAttribute(k_emit2<128, 36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
 }
 
-// Enqueue the whole pipeline for nb blocks of size g.bs starting at d_pcm.
-static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int nb, uint32_t first_frame, uint64_t frame_index0,
-                      uint8_t *d_out, size_t out_cap, unsigned long long *d_offsets, cudaStream_t st)
+static void use_ws(fb200_encoder *e, int b)
+{
+	e->d_sig = e->ws[b].d_sig; e->d_meta = e->ws[b].d_meta; e->d_blkflags = e->ws[b].d_blkflags;
+	e->d_autoc = e->ws[b].d_autoc; e->d_cdesc = e->ws[b].d_cdesc;
+}
+
+// Stage A of nb blocks of size g.bs starting at d_pcm: k_prep, k_autoc, k_lpc (writes the current workspace set).
+static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int nb, cudaStream_t st)
 {
 	EncK k = g.k;
-	k.first_frame = first_frame;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
 	k_prep<<<nb, 256, 0, st>>>(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags);
@@ -356,6 +366,18 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
+	FB_CUDA(cudaGetLastError());
+	return FB200_OK;
+}
+
+// Stage B: k_search, k_emit, k_scan, k_gather (reads the current workspace set).
+static int run_stage_b(fb200_encoder *e, Geometry &g, int nb, uint32_t first_frame, uint64_t frame_index0,
+                       uint8_t *d_out, size_t out_cap, unsigned long long *d_offsets, cudaStream_t st)
+{
+	EncK k = g.k;
+	k.first_frame = first_frame;
+	const int nitems = nb * k.nsig;
+	prof_mark(e, -1, st);
 	if(g.fast_search3 && !e->use_v1 && e->search_version >= 3) {
 		if(g.maxord_t == 8) launch_search3<8>(k, e, g, nitems, st);
 		else if(g.maxord_t == 12) launch_search3<12>(k, e, g, nitems, st);
@@ -381,6 +403,29 @@ static int run_blocks(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int n
 	prof_mark(e, FB200_PROF_GATHER, st);
 	e->launches += 4;
 	FB_CUDA(cudaGetLastError());
+	return FB200_OK;
+}
+
+struct PipeChunk { uint64_t first; uint32_t nb; uint32_t blocksize; cudaEvent_t wait_before_a; };
+
+// Enqueue chunk `idx` of a call: stage A on e->s_a, stage B on `sb`; consecutive chunks alternate workspace sets.
+static int enqueue_chunk(fb200_encoder *e, size_t idx, const PipeChunk &c, const int32_t *d_pcm_base, uint32_t first_frame_number,
+                         uint8_t *d_out, size_t out_cap, unsigned long long *d_offsets, cudaStream_t sb)
+{
+	const uint32_t bs = e->cfg.blocksize, ch = e->cfg.channels;
+	const int b = (int)(idx & 1);
+	Geometry *g = nullptr;
+	int rc;
+	if((rc = build_geometry(e, (int)c.blocksize, &g)) != FB200_OK) return rc;
+	if(c.wait_before_a) FB_CUDA(cudaStreamWaitEvent(e->s_a, c.wait_before_a, 0));
+	if(e->ev_b_valid[b]) FB_CUDA(cudaStreamWaitEvent(e->s_a, e->ev_b[b], 0));  // stage B two chunks ago is done with this set
+	use_ws(e, b);
+	if((rc = run_stage_a(e, *g, d_pcm_base + (size_t)c.first * bs * ch, (int)c.nb, e->s_a)) != FB200_OK) return rc;
+	FB_CUDA(cudaEventRecord(e->ev_a[b], e->s_a));
+	FB_CUDA(cudaStreamWaitEvent(sb, e->ev_a[b], 0));
+	if((rc = run_stage_b(e, *g, (int)c.nb, first_frame_number + (uint32_t)c.first, c.first, d_out, out_cap, d_offsets, sb)) != FB200_OK) return rc;
+	FB_CUDA(cudaEventRecord(e->ev_b[b], sb));
+	e->ev_b_valid[b] = true;
 	return FB200_OK;
 }
 
@@ -514,11 +559,14 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 			return FB200_ERR_ALLOC;                                                           \
 		}                                                                                     \
 	} while(0)
-	ALLOC(e->d_sig, (nitems * bs_stride + 1024) * sizeof(int32_t));  // + slack: k_autoc2 reads whole int4 bodies past the last run
-	ALLOC(e->d_meta, nitems * sizeof(SigMeta));
-	ALLOC(e->d_blkflags, nb * sizeof(int));
-	ALLOC(e->d_autoc, (e->max_nsec ? e->max_nsec : 1) * nitems * e->lag_stride * sizeof(double));
-	ALLOC(e->d_cdesc, (e->max_nslots ? e->max_nslots : 1) * nitems * sizeof(CandDesc));
+	for(int b = 0; b < 2; b++) {
+		ALLOC(e->ws[b].d_sig, (nitems * bs_stride + 1024) * sizeof(int32_t));  // + slack: k_autoc2 reads whole int4 bodies past the last run
+		ALLOC(e->ws[b].d_meta, nitems * sizeof(SigMeta));
+		ALLOC(e->ws[b].d_blkflags, nb * sizeof(int));
+		ALLOC(e->ws[b].d_autoc, (e->max_nsec ? e->max_nsec : 1) * nitems * e->lag_stride * sizeof(double));
+		ALLOC(e->ws[b].d_cdesc, (e->max_nslots ? e->max_nslots : 1) * nitems * sizeof(CandDesc));
+	}
+	use_ws(e, 0);
 	ALLOC(e->d_plans, nitems * sizeof(SubframePlan));
 	ALLOC(e->d_slots, nb * slot);
 	ALLOC(e->d_frame_bytes, nb * sizeof(uint32_t));
@@ -526,7 +574,11 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	ALLOC(e->d_running, sizeof(unsigned long long));
 	ALLOC(e->d_err, sizeof(int));
 #undef ALLOC
-	if(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+	if(cudaStreamCreateWithFlags(&e->s_a, cudaStreamNonBlocking) != cudaSuccess ||
+	   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+	   cudaEventCreateWithFlags(&e->ev_a[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_a[1], cudaEventDisableTiming) != cudaSuccess ||
+	   cudaEventCreateWithFlags(&e->ev_b[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_b[1], cudaEventDisableTiming) != cudaSuccess ||
+	   cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
 		set_error("cudaStreamCreate failed");
 		fb200_encoder_destroy(e);
 		return FB200_ERR_CUDA;
@@ -566,7 +618,13 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	for(auto &kv : e->geoms) {
 		cudaFree(kv.second.d_windows); cudaFree(kv.second.d_secs); cudaFree(kv.second.d_cands);
 	}
-	cudaFree(e->d_sig); cudaFree(e->d_meta); cudaFree(e->d_blkflags); cudaFree(e->d_autoc); cudaFree(e->d_cdesc);
+	for(int b = 0; b < 2; b++) {
+		cudaFree(e->ws[b].d_sig); cudaFree(e->ws[b].d_meta); cudaFree(e->ws[b].d_blkflags); cudaFree(e->ws[b].d_autoc); cudaFree(e->ws[b].d_cdesc);
+		if(e->ev_a[b]) cudaEventDestroy(e->ev_a[b]);
+		if(e->ev_b[b]) cudaEventDestroy(e->ev_b[b]);
+	}
+	if(e->ev_fork) cudaEventDestroy(e->ev_fork);
+	if(e->s_a) cudaStreamDestroy(e->s_a);
 	cudaFree(e->d_plans); cudaFree(e->d_slots); cudaFree(e->d_frame_bytes); cudaFree(e->d_chan_assign);
 	cudaFree(e->d_running); cudaFree(e->d_err);
 	cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_offsets);
@@ -605,19 +663,20 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
 	unsigned long long *offs = reinterpret_cast<unsigned long long *>(d_frame_offsets);
 	if(samples == 0) FB_CUDA(cudaMemsetAsync(offs, 0, sizeof(unsigned long long), st));
-	Geometry *g = nullptr;
-	int rc;
-	uint64_t done = 0;
-	while(done < nfull) {
-		const int nb = (int)((nfull - done) < e->max_blocks ? (nfull - done) : e->max_blocks);
-		if((rc = build_geometry(e, (int)bs, &g)) != FB200_OK) return rc;
-		if((rc = run_blocks(e, *g, d_pcm + done * bs * ch, nb, first_frame_number + (uint32_t)done, done, d_out, out_capacity, offs, st)) != FB200_OK) return rc;
-		done += nb;
-	}
-	if(tail) {
-		// last, short block: own window tables and header blocksize (stream_encoder.c:1703-1711)
-		if((rc = build_geometry(e, (int)tail, &g)) != FB200_OK) return rc;
-		if((rc = run_blocks(e, *g, d_pcm + nfull * bs * ch, 1, first_frame_number + (uint32_t)nfull, nfull, d_out, out_capacity, offs, st)) != FB200_OK) return rc;
+	// sub-batches: ~4 per call (at most max_blocks each) so that stage A of one overlaps stage B of the previous
+	uint64_t chunk = (nfull + 3) / 4;
+	if(chunk < 512) chunk = 512;
+	if(chunk > e->max_blocks) chunk = e->max_blocks;
+	std::vector<PipeChunk> chunks;
+	for(uint64_t done = 0; done < nfull; done += chunk)
+		chunks.push_back(PipeChunk{done, (uint32_t)((nfull - done) < chunk ? (nfull - done) : chunk), bs, nullptr});
+	if(tail) chunks.push_back(PipeChunk{nfull, 1, tail, nullptr});  // short last block: own windows / header blocksize (stream_encoder.c:1703-1711)
+	FB_CUDA(cudaEventRecord(e->ev_fork, st));
+	FB_CUDA(cudaStreamWaitEvent(e->s_a, e->ev_fork, 0));
+	e->ev_b_valid[0] = e->ev_b_valid[1] = false;
+	for(size_t i = 0; i < chunks.size(); i++) {
+		const int rc = enqueue_chunk(e, i, chunks[i], d_pcm, first_frame_number, d_out, out_capacity, offs, st);
+		if(rc != FB200_OK) return rc;
 	}
 	if(sync) {
 		FB_CUDA(cudaStreamSynchronize(st));
@@ -668,11 +727,10 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 	uint64_t chunk = (nfull + 4) / 5;
 	if(chunk < 256) chunk = 256;
 	if(chunk > e->max_blocks) chunk = e->max_blocks;
-	struct Chunk { uint64_t first; uint32_t nb; uint32_t blocksize; };
-	std::vector<Chunk> chunks;
+	std::vector<PipeChunk> chunks;
 	for(uint64_t done = 0; done < nfull; done += chunk)
-		chunks.push_back(Chunk{done, (uint32_t)((nfull - done) < chunk ? (nfull - done) : chunk), bs});
-	if(tail) chunks.push_back(Chunk{nfull, 1, tail});
+		chunks.push_back(PipeChunk{done, (uint32_t)((nfull - done) < chunk ? (nfull - done) : chunk), bs, nullptr});
+	if(tail) chunks.push_back(PipeChunk{nfull, 1, tail, nullptr});
 	const size_t used = chunks.size();
 	if(used > e->h_totals_cap) {
 		if(e->h_totals) cudaFreeHost(e->h_totals);
@@ -689,17 +747,16 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 	cudaStream_t sc = e->stream;
 	FB_CUDA(cudaMemsetAsync(e->d_running, 0, sizeof(unsigned long long), sc));
 	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), sc));
+	e->ev_b_valid[0] = e->ev_b_valid[1] = false;
 	for(size_t ci = 0; ci < used; ci++) {
-		const Chunk &c = chunks[ci];
+		PipeChunk &c = chunks[ci];
 		const size_t off_elems = (size_t)c.first * bs * ch;
 		const size_t nsamp = (size_t)c.nb * c.blocksize;
-		Geometry *g = nullptr;
-		int rc;
 		FB_CUDA(cudaMemcpyAsync(e->d_pcm + off_elems, pcm + off_elems, nsamp * ch * sizeof(int32_t), cudaMemcpyHostToDevice, e->s_h2d));
 		FB_CUDA(cudaEventRecord(e->ev_h2d[ci], e->s_h2d));
-		FB_CUDA(cudaStreamWaitEvent(sc, e->ev_h2d[ci], 0));
-		if((rc = build_geometry(e, (int)c.blocksize, &g)) != FB200_OK) return rc;
-		if((rc = run_blocks(e, *g, e->d_pcm + off_elems, (int)c.nb, first_frame_number + (uint32_t)c.first, c.first, e->d_out, e->d_out_cap, e->d_offsets, sc)) != FB200_OK) return rc;
+		c.wait_before_a = e->ev_h2d[ci];
+		const int rc = enqueue_chunk(e, ci, c, e->d_pcm, first_frame_number, e->d_out, e->d_out_cap, e->d_offsets, sc);
+		if(rc != FB200_OK) return rc;
 		FB_CUDA(cudaMemcpyAsync(&e->h_totals[ci], e->d_running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
 		FB_CUDA(cudaEventRecord(e->ev_comp[ci], sc));
 	}
