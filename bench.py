@@ -491,13 +491,16 @@ def main():
         "k_scan": 12,
         "k_gather": 2 * frame_bytes,
     }
-    traffic = ncu_traffic().get(args.workload, {})
+    traffic_per_block = ncu_traffic().get(args.workload, {})
+    traffic = {}
     total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
     kernels = {}
     for name, (ms, n) in prof.items():
         if n == 0:
             continue
         blocks_per_launch = blocks * args.steps / n
+        if isinstance(traffic_per_block.get(name), (int, float)):
+            traffic[name] = int(traffic_per_block[name] * blocks_per_launch)
         alg = per_block_bytes[name] * blocks_per_launch
         avg_ms = ms / n
         kernels[name] = {"ms_per_launch": round(avg_ms, 4), "launches": n, "share": round(ms / total_kernel_ms, 4),
