@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "fb200_internal.h"
+#include "glibc_log_data.h"
 
 namespace fb200 {
 
@@ -50,6 +51,83 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
 }
 
 __device__ __forceinline__ uint32_t abs_u32(int32_t r) { return r < 0 ? (uint32_t)0 - (uint32_t)r : (uint32_t)r; }
+
+// ================================================================ log()
+// The reference calls the HOST libm's log() on its decision path (lpc.c:1594 order guess and
+// "don't even try" tests, fixed.c:284-288). CUDA's log() is not bit-identical to glibc's, so this is an
+// operation-by-operation restatement of the routine glibc selects on x86-64 hosts with FMA+AVX2
+// (`__log_fma`, the FMA build of sysdeps/ieee754/dbl-64/e_log.c), transcribed from its disassembly:
+// the same fused and unfused operations in the same order, tables extracted from the same binary
+// (glibc_log_data.h). tests/test_gpu_log.py compares it with the host's log() bit for bit.
+__device__ __forceinline__ double fb_log(double x)
+{
+	unsigned long long ix = (unsigned long long)__double_as_longlong(x);
+	if(ix - 0x3fee000000000000ull <= 0x308ffffffffffull) {
+		// 1 - 2^-4 <= x < 1 + 0x1.09p-4: polynomial in r = x - 1 with a double-double head
+		if(ix == 0x3ff0000000000000ull) return 0.0;
+		const double r = __dsub_rn(x, 1.0);
+		double p2 = __fma_rn(r, kLogB[2], kLogB[1]);
+		double p3 = __fma_rn(r, kLogB[5], kLogB[4]);
+		const double r2 = __dmul_rn(r, r);
+		double p5 = __fma_rn(r, kLogB[8], kLogB[7]);
+		p2 = __fma_rn(r2, kLogB[3], p2);
+		p3 = __fma_rn(r2, kLogB[6], p3);
+		const double r3 = __dmul_rn(r, r2);
+		double p1 = __fma_rn(r2, kLogB[9], p5);
+		p1 = __fma_rn(r3, kLogB[10], p1);
+		p1 = __fma_rn(p1, r3, p3);
+		p1 = __fma_rn(p1, r3, p2);
+		const double t = __fma_rn(r, 134217728.0, r);        // r + r*2^27
+		const double rhi = __fma_rn(-134217728.0, r, t);     // ... - r*2^27
+		const double b0 = kLogB[0];
+		const double rhi2 = __dmul_rn(rhi, rhi);
+		const double rlo = __dsub_rn(r, rhi);
+		const double hi = __fma_rn(rhi2, b0, r);
+		const double d = __dsub_rn(r, hi);
+		const double rs = __dadd_rn(r, rhi);
+		double lo = __fma_rn(rhi2, b0, d);
+		const double brlo = __dmul_rn(b0, rlo);
+		lo = __fma_rn(brlo, rs, lo);
+		const double y = __fma_rn(p1, r3, lo);
+		return __dadd_rn(hi, y);
+	}
+	const unsigned int top = (unsigned int)(ix >> 48);
+	if(top - 0x10u > 0x7fdfu) {
+		// x <= 0, subnormal, inf or nan
+		if((ix << 1) == 0) return -CUDART_INF;
+		if(ix == 0x7ff0000000000000ull) return x;
+		if((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return CUDART_NAN;
+		x = __dmul_rn(x, 4503599627370496.0);  // subnormal: scale by 2^52
+		ix = (unsigned long long)__double_as_longlong(x) - (52ull << 52);
+	}
+	const unsigned long long tmp = ix - 0x3fe6000000000000ull;
+	const int i = (int)((tmp >> 45) & 0x7f);
+	const int k = (int)((long long)tmp >> 52);
+	const unsigned long long iz = ix - (tmp & 0xfff0000000000000ull);
+	const double invc = kLogTab[2 * i], logc = kLogTab[2 * i + 1];
+	const double z = __longlong_as_double((long long)iz);
+	const double kd = (double)k;
+	const double w = __fma_rn(kd, kLogLn2Hi, logc);
+	const double r = __fma_rn(z, invc, -1.0);
+	const double q21 = __fma_rn(r, kLogA[2], kLogA[1]);
+	const double hi = __dadd_rn(r, w);
+	const double r2 = __dmul_rn(r, r);
+	double lo = __dsub_rn(w, hi);
+	lo = __dadd_rn(lo, r);
+	lo = __fma_rn(kd, kLogLn2Lo, lo);
+	const double r3 = __dmul_rn(r, r2);
+	double q = __fma_rn(r, kLogA[4], kLogA[3]);
+	lo = __fma_rn(r2, kLogA[0], lo);
+	q = __fma_rn(q, r2, q21);
+	const double y = __fma_rn(r3, q, lo);
+	return __dadd_rn(y, hi);
+}
+
+__global__ void k_debug_log(const double *__restrict__ x, double *__restrict__ y, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) y[i] = fb_log(x[i]);
+}
 
 // ================================================================ k_prep
 // One CTA per block. Signals are stored planar as sig[(blk*nsig + s)*bs_stride + i]:
@@ -209,7 +287,7 @@ __global__ void __launch_bounds__(128) k_autoc(EncK P, const int32_t *__restrict
 __device__ __forceinline__ double expected_bits_scale(double lpc_error, double error_scale)
 {
 	if(lpc_error > 0.0) {
-		const double bps = (0.5 * log(error_scale * lpc_error)) / M_LN2;
+		const double bps = (0.5 * fb_log(error_scale * lpc_error)) / M_LN2;
 		return bps >= 0.0 ? bps : 0.0;
 	}
 	else if(lpc_error < 0.0)
@@ -588,7 +666,7 @@ __global__ void __launch_bounds__(128) k_search(EncK P, const int32_t *__restric
 			const unsigned long long tt[5] = {t0, t1, t2, t3, t4};
 #pragma unroll
 			for(int k = 0; k < 5; k++)
-				rbps[k] = (float)((tt[k] > 0) ? log(M_LN2 * (double)tt[k] / n) / M_LN2 : 0.0);
+				rbps[k] = (float)((tt[k] > 0) ? fb_log(M_LN2 * (double)tt[k] / n) / M_LN2 : 0.0);
 		}
 		bool is_constant = false;
 		if(!P.dis_const && rbps[1] == 0.0f) {

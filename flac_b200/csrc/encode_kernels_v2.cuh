@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128) k_search2(EncK P, const int32_t *__restri
 			const unsigned long long tt[5] = {t0, t1, t2, t3, t4};
 #pragma unroll
 			for(int k = 0; k < 5; k++)
-				rbps[k] = (float)((tt[k] > 0) ? log(M_LN2 * (double)tt[k] / n) / M_LN2 : 0.0);
+				rbps[k] = (float)((tt[k] > 0) ? fb_log(M_LN2 * (double)tt[k] / n) / M_LN2 : 0.0);
 		}
 		bool is_constant = false;
 		if(!P.dis_const && rbps[1] == 0.0f) {

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 			const double n = (double)(uint32_t)(bs - (int)kMaxFixedOrder);
 #pragma unroll
 			for(int k = 0; k < 5; k++)
-				rbps[k] = (float)((te[k] > 0) ? log(M_LN2 * (double)te[k] / n) / M_LN2 : 0.0);
+				rbps[k] = (float)((te[k] > 0) ? fb_log(M_LN2 * (double)te[k] / n) / M_LN2 : 0.0);
 		}
 		const bool is_constant = !P.dis_const && rbps[1] == 0.0f && eq;
 		if(is_constant) {

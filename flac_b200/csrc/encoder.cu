@@ -799,6 +799,21 @@ int fb200_encoder_get_profile(fb200_encoder *e, double ms[FB200_PROF_KERNELS], u
 	return FB200_OK;
 }
 
+// device restatement of the host libm's log() vs the host's own (tests/test_gpu_log.py)
+int fb200_debug_log(const double *x, double *y, uint32_t n, int device)
+{
+	if(!x || !y) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(device));
+	double *dx = nullptr, *dy = nullptr;
+	FB_CUDA(cudaMalloc(&dx, (size_t)n * sizeof(double)));
+	FB_CUDA(cudaMalloc(&dy, (size_t)n * sizeof(double)));
+	FB_CUDA(cudaMemcpy(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+	k_debug_log<<<(n + 255) / 256, 256>>>(dx, dy, (int)n);
+	FB_CUDA(cudaMemcpy(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+	cudaFree(dx); cudaFree(dy);
+	return FB200_OK;
+}
+
 // ---- debug/stage-level access for the parity tests (plans of the last launch) ----
 int fb200_debug_copy_plans(fb200_encoder *e, uint32_t nblocks, void *host_plans, size_t plan_bytes, uint32_t *host_chan_assign)
 {

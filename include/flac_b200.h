@@ -130,6 +130,8 @@ int fb200_encoder_get_profile(fb200_encoder *enc, double ms[FB200_PROF_KERNELS],
 /* Stage-level debug access used by the parity tests: the per-signal decisions (fb200::SubframePlan,
  * flac_b200/csrc/fb200_internal.h) and channel assignments of the most recent launch. */
 int fb200_debug_copy_plans(fb200_encoder *enc, uint32_t nblocks, void *host_plans, size_t plan_bytes, uint32_t *host_chan_assign);
+/* y[i] = the engine's device restatement of the host libm's log(x[i]) (reference: lpc.c:1594, fixed.c:284). */
+int fb200_debug_log(const double *x, double *y, uint32_t n, int device);
 
 /* ---- decoder ----
  * Batch frame decode (read_frame_ for many frames). The caller supplies frame boundaries

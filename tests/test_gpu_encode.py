@@ -158,3 +158,16 @@ def test_big_batch_property_round_trip():
         y = oraclelib.decode_frames(fr, 2, 16, 44100, 4096)
         assert np.array_equal(y, x[i * 4096:(i + 1) * 4096]), f"frame {i}"
     enc.close()
+
+
+@pytest.mark.parametrize("env", [{"FB200_FORCE_GENERAL_KERNELS": "1"}, {"FB200_SEARCH_KERNEL": "2"}, {"FB200_SEARCH_KERNEL": "1"},
+                                 {"FB200_AUTOC_SPLIT": "1"}])
+@pytest.mark.parametrize("level,ch,bps", [(8, 2, 16), (5, 2, 16), (8, 2, 24), (2, 1, 16)])
+def test_every_kernel_generation_is_bit_exact(env, level, ch, bps, monkeypatch):
+    """The general kernels (any blocksize), the v2 CTA-per-signal search and the split autocorrelation are
+    selectable at encoder creation; each must reproduce the oracle's frames on standard blocksizes too."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    x = signals.music_like(4096 * 3 + 55, ch, bps, 44100, seed=17)
+    got = _gpu_frames(x, bps, 44100, level)
+    _assert_same(got, _oracle_frames(x, bps, 44100, level), f"{env}")
