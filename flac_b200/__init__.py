@@ -29,7 +29,7 @@ class FlacB200Error(RuntimeError):
 
 
 class Apodization(C.Structure):
-    _fields_ = [("type", C.c_int32), ("p", C.c_float), ("parts", C.c_int32)]
+    _fields_ = [("type", C.c_int32), ("p", C.c_float), ("parts", C.c_int32), ("start", C.c_float), ("end", C.c_float)]
 
 
 class EncoderConfig(C.Structure):
@@ -75,6 +75,10 @@ def lib():
     L.fb200_device_count.restype = C.c_int
     L.fb200_encoder_config_preset.restype = C.c_int
     L.fb200_encoder_config_preset.argtypes = [C.POINTER(EncoderConfig), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.fb200_encoder_config_set_apodization.restype = C.c_int
+    L.fb200_encoder_config_set_apodization.argtypes = [C.POINTER(EncoderConfig), C.c_char_p]
+    L.fb200_window.restype = C.c_int
+    L.fb200_window.argtypes = [C.POINTER(Apodization), C.c_int32, C.c_void_p]
     L.fb200_encoder_create.restype = C.c_int
     L.fb200_encoder_create.argtypes = [C.POINTER(EncoderConfig), C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
     L.fb200_encoder_destroy.argtypes = [C.c_void_p]
@@ -125,8 +129,18 @@ def preset(channels, bits_per_sample, sample_rate, compression_level, blocksize=
     cfg = EncoderConfig()
     _check(lib().fb200_encoder_config_preset(C.byref(cfg), channels, bits_per_sample, sample_rate, compression_level, blocksize))
     for k, v in overrides.items():
-        setattr(cfg, k, v)
+        if k == "apodization":  # == FLAC__stream_encoder_set_apodization(specification string)
+            _check(lib().fb200_encoder_config_set_apodization(C.byref(cfg), v.encode() if isinstance(v, str) else v))
+        else:
+            setattr(cfg, k, v)
     return cfg
+
+
+def window(apodization, length):
+    """The float window table the encoder uploads for one Apodization at this block length."""
+    out = np.empty(length, dtype=np.float32)
+    _check(lib().fb200_window(C.byref(apodization), length, out.ctypes.data))
+    return out
 
 
 class Encoder:

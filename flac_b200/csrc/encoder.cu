@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "encode_kernels_v3.cuh"
+#include "windows.h"
 
 namespace fb200 {
 
@@ -27,31 +28,6 @@ void set_error(const char *fmt, ...)
 	va_end(ap);
 }
 const char *get_error() { return g_err; }
-
-// src/libFLAC/window.c:46-55, 136-143, 195-220 (FLAC__window_rectangle / _hann / _tukey)
-static void window_tukey(float *window, int32_t L, float p)
-{
-	if(p <= 0.0) {
-		for(int32_t n = 0; n < L; n++) window[n] = 1.0f;
-	}
-	else if(p >= 1.0) {
-		const int32_t N = L - 1;
-		for(int32_t n = 0; n < L; n++) window[n] = (float)(0.5f - 0.5f * cosf(2.0f * M_PI * n / N));
-	}
-	else if(!(p > 0.0f && p < 1.0f)) {
-		window_tukey(window, L, 0.5f);
-	}
-	else {
-		const int32_t Np = (int32_t)(p / 2.0f * L) - 1;
-		for(int32_t n = 0; n < L; n++) window[n] = 1.0f;
-		if(Np > 0) {
-			for(int32_t n = 0; n <= Np; n++) {
-				window[n] = (float)(0.5f - 0.5f * cosf(M_PI * n / Np));
-				window[L - Np - 1 + n] = (float)(0.5f - 0.5f * cosf(M_PI * (n + Np) / Np));
-			}
-		}
-	}
-}
 
 struct Geometry {
 	int bs = 0;
@@ -196,7 +172,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 			const fb200_apodization &ap = c.apodizations[a];
 			const int win_off = (int)windows.size();
 			windows.resize(windows.size() + bs);
-			window_tukey(windows.data() + win_off, bs, ap.p);  // resize_buffers_, stream_encoder.c:2956-2967
+			fbwin::make(ap, windows.data() + win_off, bs);  // resize_buffers_, stream_encoder.c:2913-2975
 			const int root = (int)secs.size();
 			secs.push_back(DevSection{win_off, 0, bs, 0, 0});
 			cands.push_back(DevCand{0, root, root});
@@ -472,6 +448,82 @@ int fb200_encoder_config_preset(fb200_encoder_config *cfg, uint32_t channels, ui
 	return FB200_OK;
 }
 
+// FLAC__stream_encoder_set_apodization (stream_encoder.c:1940-2065): ';'-separated window names.
+// Unknown names are skipped; an empty result falls back to tukey(0.5); at most 32 windows.
+// Kept quirks: the '/' separators of the *_tukey(...) forms are searched with strchr from the
+// start of the current item to the end of the whole string (:1994, :2015, :2037), and
+// partial_/punchout_tukey expand only while num + parts < 32 (:2004, :2025).
+int fb200_encoder_config_set_apodization(fb200_encoder_config *cfg, const char *spec)
+{
+	if(!cfg || !spec) return FB200_ERR_INVALID;
+	static const struct { const char *name; int32_t type; } plain[] = {
+		{"bartlett", FB200_APOD_BARTLETT}, {"bartlett_hann", FB200_APOD_BARTLETT_HANN}, {"blackman", FB200_APOD_BLACKMAN},
+		{"blackman_harris_4term_92db", FB200_APOD_BLACKMAN_HARRIS_4TERM_92DB_SIDELOBE}, {"connes", FB200_APOD_CONNES},
+		{"flattop", FB200_APOD_FLATTOP}, {"hamming", FB200_APOD_HAMMING}, {"hann", FB200_APOD_HANN},
+		{"kaiser_bessel", FB200_APOD_KAISER_BESSEL}, {"nuttall", FB200_APOD_NUTTALL}, {"rectangle", FB200_APOD_RECTANGLE},
+		{"triangle", FB200_APOD_TRIANGLE}, {"welch", FB200_APOD_WELCH}};
+	uint32_t &num = cfg->num_apodizations;
+	num = 0;
+	auto push = [&](int32_t type, float p, int32_t parts, float start, float end) {
+		fb200_apodization &a = cfg->apodizations[num++];
+		a.type = type; a.p = p; a.parts = parts; a.start = start; a.end = end;
+	};
+	auto starts = [&](const char *prefix) { return 0 == strncmp(prefix, spec, strlen(prefix)); };
+	for(;;) {
+		const char *semi = strchr(spec, ';');
+		const size_t n = semi ? (size_t)(semi - spec) : strlen(spec);
+		bool matched = false;
+		for(const auto &pl : plain)
+			if(n == strlen(pl.name) && 0 == strncmp(pl.name, spec, n)) { push(pl.type, 0.0f, 0, 0.0f, 0.0f); matched = true; break; }
+		if(matched) {}
+		else if(n > 7 && starts("gauss(")) {
+			const float stddev = (float)strtod(spec + 6, 0);
+			if(stddev > 0.0 && stddev <= 0.5) push(FB200_APOD_GAUSS, stddev, 0, 0.0f, 0.0f);
+		}
+		else if(n > 7 && starts("tukey(")) {
+			const float p = (float)strtod(spec + 6, 0);
+			if(p >= 0.0 && p <= 1.0) push(FB200_APOD_TUKEY, p, 0, 0.0f, 0.0f);
+		}
+		else if((n > 15 && starts("partial_tukey(")) || (n > 16 && starts("punchout_tukey("))) {
+			const bool partial = spec[1] == 'a';
+			const int32_t parts = (int32_t)strtod(spec + (partial ? 14 : 15), 0);
+			const char *s1 = strchr(spec, '/');
+			const float ov_in = s1 ? (float)strtod(s1 + 1, 0) : 0.0f;
+			const float overlap = s1 ? (ov_in < 0.99f ? ov_in : 0.99f) : (partial ? 0.1f : 0.2f);
+			const float overlap_units = 1.0f / (1.0f - overlap) - 1.0f;
+			const char *s2 = strchr(s1 ? s1 + 1 : spec, '/');
+			const float tukey_p = s2 ? (float)strtod(s2 + 1, 0) : 0.2f;
+			if(parts <= 1) push(FB200_APOD_TUKEY, tukey_p, 0, 0.0f, 0.0f);
+			else if(num + parts < 32)
+				for(int32_t m = 0; m < parts; m++)
+					push(partial ? FB200_APOD_PARTIAL_TUKEY : FB200_APOD_PUNCHOUT_TUKEY, tukey_p, 0,
+					     m / (parts + overlap_units), (m + 1 + overlap_units) / (parts + overlap_units));
+		}
+		else if(n > 17 && starts("subdivide_tukey(")) {
+			const int32_t parts = (int32_t)strtod(spec + 16, 0);
+			if(parts > 1) {
+				const char *s1 = strchr(spec, '/');
+				float p = s1 ? (float)strtod(s1 + 1, 0) : 5e-1;
+				if(p > 1) p = 1;
+				else if(p < 0) p = 0;
+				push(FB200_APOD_SUBDIVIDE_TUKEY, p / parts, parts, 0.0f, 0.0f);
+			}
+		}
+		if(num == 32) break;
+		if(!semi) break;
+		spec = semi + 1;
+	}
+	if(num == 0) push(FB200_APOD_TUKEY, 0.5f, 0, 0.0f, 0.0f);
+	return FB200_OK;
+}
+
+// One window table, as the encoder uploads it (tests compare it with the reference's FLAC__window_*).
+int fb200_window(const fb200_apodization *apodization, int32_t length, float *out)
+{
+	if(!apodization || !out || length < 2) return FB200_ERR_INVALID;
+	return fbwin::make(*apodization, out, length) ? FB200_OK : FB200_ERR_INVALID;
+}
+
 int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_t max_blocks, fb200_encoder **out)
 {
 	if(!cfg_in || !out) return FB200_ERR_INVALID;
@@ -517,7 +569,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	if(c.limit_min_bitrate) { set_error("limit_min_bitrate unsupported"); return FB200_ERR_UNSUPPORTED; }
 	if(c.num_apodizations == 0 || c.num_apodizations > FB200_MAX_APODIZATIONS) { set_error("invalid number of apodizations"); return FB200_ERR_INVALID; }
 	for(uint32_t a = 0; a < c.num_apodizations; a++)
-		if(c.apodizations[a].type != FB200_APOD_TUKEY && c.apodizations[a].type != FB200_APOD_SUBDIVIDE_TUKEY) { set_error("apodization type %d unsupported", c.apodizations[a].type); return FB200_ERR_UNSUPPORTED; }
+		if(c.apodizations[a].type < FB200_APOD_TUKEY || c.apodizations[a].type > FB200_APOD_WELCH) { set_error("apodization type %d unknown", c.apodizations[a].type); return FB200_ERR_INVALID; }
 
 	int ndev = 0;
 	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

@@ -238,7 +238,6 @@ struct FLAC__StreamEncoderProtected {
 	FLAC__StreamEncoderState state;
 	FLAC__bool verify, streamable_subset, do_md5;
 	fb200_encoder_config cfg;          // every knob that reaches the frame path
-	bool apodization_unsupported;
 	FLAC__bool do_escape_coding;
 	uint32_t rice_parameter_search_dist, num_threads;
 	FLAC__uint64 total_samples_estimate;
@@ -283,7 +282,6 @@ static void enc_set_defaults(FLAC__StreamEncoder *e)
 	p->verify = false; p->streamable_subset = true; p->do_md5 = true;
 	memset(&p->cfg, 0, sizeof p->cfg);
 	fb200_encoder_config_preset(&p->cfg, 2, 16, 44100, 5, 0);
-	p->apodization_unsupported = false;
 	p->do_escape_coding = false; p->rice_parameter_search_dist = 0; p->num_threads = 1;
 	p->total_samples_estimate = 0; p->metadata = nullptr; p->num_metadata_blocks = 0;
 	FLAC__StreamEncoderPrivate *q = e->private_;
@@ -389,51 +387,15 @@ FLAC__bool FLAC__stream_encoder_set_compression_level(FLAC__StreamEncoder *e, ui
 	c.do_exhaustive_model_search = 0; c.min_residual_partition_order = 0; c.max_residual_partition_order = t.max_residual_partition_order;
 	c.num_apodizations = t.num_apodizations;
 	memcpy(c.apodizations, t.apodizations, sizeof c.apodizations);
-	e->protected_->apodization_unsupported = false;
 	e->protected_->rice_parameter_search_dist = 0;
 	return true;
 }
 
 FLAC__bool FLAC__stream_encoder_set_apodization(FLAC__StreamEncoder *e, const char *spec)
 {
-	// stream_encoder.c:1939-2065. Supported: tukey(P), subdivide_tukey(N[/P]); other known window names are
-	// remembered as unsupported (init then fails loudly); unknown strings are ignored like the reference does.
+	// stream_encoder.c:1940-2065; the parser lives with the engine configuration (encoder.cu)
 	if(e->protected_->state != FLAC__STREAM_ENCODER_UNINITIALIZED) return false;
-	fb200_encoder_config &c = e->protected_->cfg;
-	c.num_apodizations = 0;
-	e->protected_->apodization_unsupported = false;
-	static const char *known[] = {"bartlett", "bartlett_hann", "blackman", "blackman_harris_4term_92db", "connes", "flattop", "hamming", "hann",
-	                              "kaiser_bessel", "nuttall", "rectangle", "triangle", "welch"};
-	while(1) {
-		const char *s = strchr(spec, ';');
-		const size_t n = s ? (size_t)(s - spec) : strlen(spec);
-		if(n > 7 && 0 == strncmp("tukey(", spec, 6)) {
-			const float p = (float)strtod(spec + 6, 0);
-			if(p >= 0.0 && p <= 1.0) { c.apodizations[c.num_apodizations].type = FB200_APOD_TUKEY; c.apodizations[c.num_apodizations].p = p; c.apodizations[c.num_apodizations++].parts = 0; }
-		}
-		else if(n > 17 && 0 == strncmp("subdivide_tukey(", spec, 16)) {
-			const int32_t parts = (int32_t)strtod(spec + 16, 0);
-			if(parts > 1) {
-				const char *si_1 = (const char *)memchr(spec, '/', n);
-				float p = si_1 ? (float)strtod(si_1 + 1, 0) : 5e-1;
-				if(p > 1) p = 1; else if(p < 0) p = 0;
-				c.apodizations[c.num_apodizations].type = FB200_APOD_SUBDIVIDE_TUKEY;
-				c.apodizations[c.num_apodizations].parts = parts;
-				c.apodizations[c.num_apodizations++].p = p / parts;
-			}
-		}
-		else {
-			bool is_known = (n > 6 && 0 == strncmp("gauss(", spec, 6)) || (n > 15 && 0 == strncmp("partial_tukey(", spec, 14)) || (n > 16 && 0 == strncmp("punchout_tukey(", spec, 15));
-			for(const char *k : known) if(strlen(k) == n && 0 == strncmp(k, spec, n)) is_known = true;
-			if(is_known) e->protected_->apodization_unsupported = true;
-		}
-		if(c.num_apodizations == 32) break;
-		if(s) spec = s + 1; else break;
-	}
-	if(c.num_apodizations == 0 && !e->protected_->apodization_unsupported) {
-		c.num_apodizations = 1; c.apodizations[0].type = FB200_APOD_TUKEY; c.apodizations[0].p = 0.5f; c.apodizations[0].parts = 0;
-	}
-	return true;
+	return fb200_encoder_config_set_apodization(&e->protected_->cfg, spec) == FB200_OK;
 }
 
 FLAC__bool FLAC__stream_encoder_set_metadata(FLAC__StreamEncoder *e, FLAC__StreamMetadata **metadata, uint32_t num_blocks)
@@ -614,7 +576,7 @@ static FLAC__StreamEncoderInitStatus enc_init_common(FLAC__StreamEncoder *e, boo
 			has_vc = true;
 		}
 	}
-	if(p->apodization_unsupported || c.num_apodizations == 0) return FLAC__STREAM_ENCODER_INIT_STATUS_ENCODER_ERROR;
+	if(c.num_apodizations == 0) return FLAC__STREAM_ENCODER_INIT_STATUS_ENCODER_ERROR;
 
 	// ---- the engine (no CPU fallback)
 	q->batch = batch_blocks();

@@ -40,13 +40,36 @@ enum {
 };
 
 /* Apodization functions (reference: FLAC__stream_encoder_set_apodization,
- * src/libFLAC/stream_encoder.c:1939-2065; window generators src/libFLAC/window.c). */
-enum { FB200_APOD_TUKEY = 0, FB200_APOD_SUBDIVIDE_TUKEY = 1 };
+ * src/libFLAC/stream_encoder.c:1939-2065; window generators src/libFLAC/window.c:50-302).
+ * Every function the reference's specification string knows is here; the window tables are
+ * generated on the host once per blocksize (flac_b200/csrc/windows.h). */
+enum {
+	FB200_APOD_TUKEY = 0,            /* tukey(P) */
+	FB200_APOD_SUBDIVIDE_TUKEY = 1,  /* subdivide_tukey(N[/P]) */
+	FB200_APOD_BARTLETT = 2,
+	FB200_APOD_BARTLETT_HANN = 3,
+	FB200_APOD_BLACKMAN = 4,
+	FB200_APOD_BLACKMAN_HARRIS_4TERM_92DB_SIDELOBE = 5,
+	FB200_APOD_CONNES = 6,
+	FB200_APOD_FLATTOP = 7,
+	FB200_APOD_GAUSS = 8,            /* gauss(STDDEV): stddev in .p */
+	FB200_APOD_HAMMING = 9,
+	FB200_APOD_HANN = 10,
+	FB200_APOD_KAISER_BESSEL = 11,
+	FB200_APOD_NUTTALL = 12,
+	FB200_APOD_RECTANGLE = 13,
+	FB200_APOD_TRIANGLE = 14,
+	FB200_APOD_PARTIAL_TUKEY = 15,   /* one window of partial_tukey(N[/OV[/P]]): .p .start .end */
+	FB200_APOD_PUNCHOUT_TUKEY = 16,  /* one window of punchout_tukey(N[/OV[/P]]): .p .start .end */
+	FB200_APOD_WELCH = 17
+};
 
 typedef struct {
 	int32_t type;   /* FB200_APOD_* */
-	float p;        /* tukey(p); for subdivide_tukey(n/p) this is p/n as the reference stores it (:2049) */
+	float p;        /* tukey(p) / gauss(stddev); for subdivide_tukey(n/p) this is p/n as the reference stores it (:2045) */
 	int32_t parts;  /* subdivide_tukey parts */
+	float start;    /* partial_/punchout_tukey: window start as a fraction of the block (:2008, :2029) */
+	float end;      /* partial_/punchout_tukey: window end as a fraction of the block (:2009, :2030) */
 } fb200_apodization;
 
 /* One field per FLAC__stream_encoder_set_* knob that reaches the per-frame path
@@ -85,6 +108,13 @@ int fb200_device_count(void);                /* <0: FB200_ERR_CUDA */
  * (stream_encoder.c:117-140, 1873-1904) plus set_channels/bits_per_sample/sample_rate/blocksize. */
 int fb200_encoder_config_preset(fb200_encoder_config *cfg, uint32_t channels, uint32_t bits_per_sample,
                                 uint32_t sample_rate, uint32_t compression_level, uint32_t blocksize);
+
+/* FLAC__stream_encoder_set_apodization (stream_encoder.c:1940-2065): parse a ';'-separated
+ * specification ("tukey(0.5);partial_tukey(2);gauss(0.2);hann" ...) into cfg->apodizations. */
+int fb200_encoder_config_set_apodization(fb200_encoder_config *cfg, const char *specification);
+/* The window table the encoder uploads for one apodization at block length `length`
+ * (FLAC__window_* of src/libFLAC/window.c); host-side, needs no GPU. */
+int fb200_window(const fb200_apodization *apodization, int32_t length, float *out);
 
 /* Validates like init_stream_internal_ (stream_encoder.c:725-830), resolves blocksize and
  * qlp precision defaults, uploads window tables, sizes device workspaces for up to

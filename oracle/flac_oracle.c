@@ -7,7 +7,7 @@
  * evaluated in source order (compile with -ffp-contract=off, no fast-math).
  *
  * Scope: bits_per_sample 4..24 (subframe bps <= 25, i.e. no 33-bit side channel),
- * apodizations tukey(p) and subdivide_tukey(n[/p]) (all presets -0..-8), no escape
+ * every apodization function of the specification string, no escape
  * coding / rice parameter search (both compiled out of the reference:
  * stream_encoder.c:77-82, 2107-2114).
  */
@@ -202,6 +202,186 @@ void fo_window_tukey(float *window, int32_t L, float p)
 			}
 		}
 	}
+}
+
+/* window.c:50-197, 224-302: the other generators. Sub-expression types as C promotes them
+ * in the reference (float * double M_PI -> double, narrowed to float by cosf's prototype). */
+static float half_cos(int32_t i, int32_t Np) { return (float)(0.5f - 0.5f * cosf(M_PI * i / Np)); }
+
+int fo_window(const fo_apodization *a, float *w, int32_t L)
+{
+	const int32_t N = L - 1;
+	const double N2 = (double)N / 2.;
+	int32_t n, i;
+	switch(a->type) {
+		case FO_APOD_TUKEY:
+		case FO_APOD_SUBDIVIDE_TUKEY: /* stream_encoder.c:2962-2964 */
+			fo_window_tukey(w, L, a->p);
+			return 1;
+		case FO_APOD_BARTLETT: /* :50-67 */
+			if(L & 1) {
+				for(n = 0; n <= N / 2; n++) w[n] = 2.0f * n / (float)N;
+				for(; n <= N; n++) w[n] = 2.0f - 2.0f * n / (float)N;
+			}
+			else {
+				for(n = 0; n <= L / 2 - 1; n++) w[n] = 2.0f * n / (float)N;
+				for(; n <= N; n++) w[n] = 2.0f - 2.0f * n / (float)N;
+			}
+			return 1;
+		case FO_APOD_BARTLETT_HANN: /* :69-76 */
+			for(n = 0; n < L; n++)
+				w[n] = (float)(0.62f - 0.48f * fabsf((float)n / (float)N - 0.5f) - 0.38f * cosf(2.0f * M_PI * ((float)n / (float)N)));
+			return 1;
+		case FO_APOD_BLACKMAN: /* :78-85 */
+			for(n = 0; n < L; n++) w[n] = (float)(0.42f - 0.5f * cosf(2.0f * M_PI * n / N) + 0.08f * cosf(4.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_BLACKMAN_HARRIS: /* :88-95 */
+			for(n = 0; n <= N; n++)
+				w[n] = (float)(0.35875f - 0.48829f * cosf(2.0f * M_PI * n / N) + 0.14128f * cosf(4.0f * M_PI * n / N) - 0.01168f * cosf(6.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_CONNES: /* :97-108 */
+			for(n = 0; n <= N; n++) {
+				double k = ((double)n - N2) / N2;
+				k = 1.0f - k * k;
+				w[n] = (float)(k * k);
+			}
+			return 1;
+		case FO_APOD_FLATTOP: /* :110-117 */
+			for(n = 0; n < L; n++)
+				w[n] = (float)(0.21557895f - 0.41663158f * cosf(2.0f * M_PI * n / N) + 0.277263158f * cosf(4.0f * M_PI * n / N) - 0.083578947f * cosf(6.0f * M_PI * n / N) + 0.006947368f * cosf(8.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_GAUSS: { /* :119-135 */
+			const float stddev = (a->p > 0.0f && a->p <= 0.5f) ? a->p : 0.25f;
+			for(n = 0; n <= N; n++) {
+				const double k = ((double)n - N2) / (stddev * N2);
+				w[n] = (float)exp(-0.5f * k * k);
+			}
+			return 1;
+		}
+		case FO_APOD_HAMMING: /* :137-144 */
+			for(n = 0; n < L; n++) w[n] = (float)(0.54f - 0.46f * cosf(2.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_HANN: /* :146-153 */
+			for(n = 0; n < L; n++) w[n] = (float)(0.5f - 0.5f * cosf(2.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_KAISER_BESSEL: /* :155-162 */
+			for(n = 0; n < L; n++)
+				w[n] = (float)(0.402f - 0.498f * cosf(2.0f * M_PI * n / N) + 0.098f * cosf(4.0f * M_PI * n / N) - 0.001f * cosf(6.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_NUTTALL: /* :164-171 */
+			for(n = 0; n < L; n++)
+				w[n] = (float)(0.3635819f - 0.4891775f * cosf(2.0f * M_PI * n / N) + 0.1365995f * cosf(4.0f * M_PI * n / N) - 0.0106411f * cosf(6.0f * M_PI * n / N));
+			return 1;
+		case FO_APOD_RECTANGLE: /* :173-179 */
+			for(n = 0; n < L; n++) w[n] = 1.0f;
+			return 1;
+		case FO_APOD_TRIANGLE: /* :181-197 */
+			for(n = 1; n <= ((L & 1) ? (L + 1) / 2 : L / 2); n++) w[n - 1] = 2.0f * n / ((float)L + 1.0f);
+			for(; n <= L; n++) w[n - 1] = (float)(2 * (L - n + 1)) / ((float)L + 1.0f);
+			return 1;
+		case FO_APOD_WELCH: /* :292-302 */
+			for(n = 0; n <= N; n++) {
+				const double k = ((double)n - N2) / N2;
+				w[n] = (float)(1.0f - k * k);
+			}
+			return 1;
+		case FO_APOD_PARTIAL_TUKEY:
+		case FO_APOD_PUNCHOUT_TUKEY: {
+			/* :231-238 / :262-269 parameter clamps */
+			float p = a->p;
+			const int32_t start_n = (int32_t)(a->start * L), end_n = (int32_t)(a->end * L);
+			if(p <= 0.0f) p = 0.05f;
+			else if(p >= 1.0f) p = 0.95f;
+			else if(!(p > 0.0f && p < 1.0f)) p = 0.5f;
+			if(a->type == FO_APOD_PARTIAL_TUKEY) { /* :224-254 */
+				const int32_t Np = (int32_t)(p / 2.0f * (end_n - start_n));
+				for(n = 0; n < start_n && n < L; n++) w[n] = 0.0f;
+				for(i = 1; n < (start_n + Np) && n < L; n++, i++) w[n] = half_cos(i, Np);
+				for(; n < (end_n - Np) && n < L; n++) w[n] = 1.0f;
+				for(i = Np; n < end_n && n < L; n++, i--) w[n] = half_cos(i, Np);
+				for(; n < L; n++) w[n] = 0.0f;
+			}
+			else { /* :256-290 */
+				const int32_t Ns = (int32_t)(p / 2.0f * start_n), Ne = (int32_t)(p / 2.0f * (L - end_n));
+				for(n = 0, i = 1; n < Ns && n < L; n++, i++) w[n] = half_cos(i, Ns);
+				for(; n < start_n - Ns && n < L; n++) w[n] = 1.0f;
+				for(i = Ns; n < start_n && n < L; n++, i--) w[n] = half_cos(i, Ns);
+				for(; n < end_n && n < L; n++) w[n] = 0.0f;
+				for(i = 1; n < end_n + Ne && n < L; n++, i++) w[n] = half_cos(i, Ne);
+				for(; n < L - Ne && n < L; n++) w[n] = 1.0f;
+				for(i = Ne; n < L; n++, i--) w[n] = half_cos(i, Ne);
+			}
+			return 1;
+		}
+	}
+	return 0;
+}
+
+/* stream_encoder.c:1940-2065 FLAC__stream_encoder_set_apodization */
+void fo_config_set_apodization(fo_config *cfg, const char *spec)
+{
+	static const struct { const char *name; int32_t type; } names[] = {
+		{"bartlett", FO_APOD_BARTLETT}, {"bartlett_hann", FO_APOD_BARTLETT_HANN}, {"blackman", FO_APOD_BLACKMAN},
+		{"blackman_harris_4term_92db", FO_APOD_BLACKMAN_HARRIS}, {"connes", FO_APOD_CONNES}, {"flattop", FO_APOD_FLATTOP},
+		{"hamming", FO_APOD_HAMMING}, {"hann", FO_APOD_HANN}, {"kaiser_bessel", FO_APOD_KAISER_BESSEL}, {"nuttall", FO_APOD_NUTTALL},
+		{"rectangle", FO_APOD_RECTANGLE}, {"triangle", FO_APOD_TRIANGLE}, {"welch", FO_APOD_WELCH}};
+	fo_apodization *A = cfg->apodizations;
+	uint32_t num = 0;
+	memset(A, 0, sizeof cfg->apodizations);
+	while(1) {
+		const char *s = strchr(spec, ';');
+		const size_t n = s ? (size_t)(s - spec) : strlen(spec);
+		size_t t;
+		int hit = 0;
+		for(t = 0; t < sizeof names / sizeof names[0]; t++)
+			if(n == strlen(names[t].name) && 0 == strncmp(names[t].name, spec, n)) { A[num++].type = names[t].type; hit = 1; break; }
+		if(hit) {}
+		else if(n > 7 && 0 == strncmp("gauss(", spec, 6)) {
+			float stddev = (float)strtod(spec + 6, 0);
+			if(stddev > 0.0 && stddev <= 0.5) { A[num].p = stddev; A[num++].type = FO_APOD_GAUSS; }
+		}
+		else if(n > 7 && 0 == strncmp("tukey(", spec, 6)) {
+			float p = (float)strtod(spec + 6, 0);
+			if(p >= 0.0 && p <= 1.0) { A[num].p = p; A[num++].type = FO_APOD_TUKEY; }
+		}
+		else if((n > 15 && 0 == strncmp("partial_tukey(", spec, 14)) || (n > 16 && 0 == strncmp("punchout_tukey(", spec, 15))) {
+			const int partial = (spec[1] == 'a');
+			int32_t parts = (int32_t)strtod(spec + (partial ? 14 : 15), 0), m;
+			const char *si_1 = strchr(spec, '/');
+			float overlap = si_1 ? (float)strtod(si_1 + 1, 0) : (partial ? 0.1f : 0.2f);
+			float overlap_units, tukey_p;
+			const char *si_2;
+			if(si_1 && !(overlap < 0.99f)) overlap = 0.99f;
+			overlap_units = 1.0f / (1.0f - overlap) - 1.0f;
+			si_2 = strchr((si_1 ? (si_1 + 1) : spec), '/');
+			tukey_p = si_2 ? (float)strtod(si_2 + 1, 0) : 0.2f;
+			if(parts <= 1) { A[num].p = tukey_p; A[num++].type = FO_APOD_TUKEY; }
+			else if(num + parts < 32)
+				for(m = 0; m < parts; m++) {
+					A[num].p = tukey_p;
+					A[num].start = m / (parts + overlap_units);
+					A[num].end = (m + 1 + overlap_units) / (parts + overlap_units);
+					A[num++].type = partial ? FO_APOD_PARTIAL_TUKEY : FO_APOD_PUNCHOUT_TUKEY;
+				}
+		}
+		else if(n > 17 && 0 == strncmp("subdivide_tukey(", spec, 16)) {
+			int32_t parts = (int32_t)strtod(spec + 16, 0);
+			if(parts > 1) {
+				const char *si_1 = strchr(spec, '/');
+				float p = si_1 ? (float)strtod(si_1 + 1, 0) : 5e-1;
+				if(p > 1) p = 1;
+				else if(p < 0) p = 0;
+				A[num].parts = parts;
+				A[num].p = p / parts;
+				A[num++].type = FO_APOD_SUBDIVIDE_TUKEY;
+			}
+		}
+		if(num == 32) break;
+		if(s) spec = s + 1;
+		else break;
+	}
+	if(num == 0) { num = 1; A[0].type = FO_APOD_TUKEY; A[0].p = 0.5f; }
+	cfg->num_apodizations = num;
 }
 
 /* ------------------------------------------------------------------ LPC analysis */
@@ -1052,7 +1232,7 @@ static void ensure_windows(fo_encoder *e, uint32_t blocksize)
 	if(e->win_blocksize == blocksize) return;
 	if(e->cfg.max_lpc_order > 0 && blocksize > 1)
 		for(i = 0; i < e->cfg.num_apodizations; i++)
-			fo_window_tukey(e->window[i], (int32_t)blocksize, e->cfg.apodizations[i].p);
+			fo_window(&e->cfg.apodizations[i], e->window[i], (int32_t)blocksize);
 	e->win_blocksize = blocksize;
 }
 

@@ -29,12 +29,19 @@ extern "C" {
 #define FO_MAX_APODIZATIONS 32
 #define FO_MAX_PARTITIONS 256 /* partition order <= 8 */
 
-enum { FO_APOD_TUKEY = 0, FO_APOD_SUBDIVIDE_TUKEY = 1 };
+/* FLAC__ApodizationFunction (src/libFLAC/include/protected/stream_encoder.h:45-65), oracle numbering */
+enum {
+	FO_APOD_TUKEY = 0, FO_APOD_SUBDIVIDE_TUKEY = 1, FO_APOD_BARTLETT = 2, FO_APOD_BARTLETT_HANN = 3, FO_APOD_BLACKMAN = 4,
+	FO_APOD_BLACKMAN_HARRIS = 5, FO_APOD_CONNES = 6, FO_APOD_FLATTOP = 7, FO_APOD_GAUSS = 8, FO_APOD_HAMMING = 9, FO_APOD_HANN = 10,
+	FO_APOD_KAISER_BESSEL = 11, FO_APOD_NUTTALL = 12, FO_APOD_RECTANGLE = 13, FO_APOD_TRIANGLE = 14, FO_APOD_PARTIAL_TUKEY = 15,
+	FO_APOD_PUNCHOUT_TUKEY = 16, FO_APOD_WELCH = 17
+};
 
 typedef struct {
 	int32_t type;   /* FO_APOD_* */
-	float p;        /* tukey p (for subdivide: already divided by parts) */
+	float p;        /* tukey p (for subdivide: already divided by parts); gauss stddev */
 	int32_t parts;  /* subdivide_tukey parts */
+	float start, end; /* partial_/punchout_tukey extents (fractions of the block) */
 } fo_apodization;
 
 typedef struct {
@@ -96,6 +103,8 @@ int fo_encode_stream(fo_encoder *e, const int32_t *interleaved, uint64_t samples
 
 /* Stage-level entry points (same arithmetic the frame encoder uses). */
 void fo_window_tukey(float *window, int32_t L, float p);
+int fo_window(const fo_apodization *a, float *window, int32_t L);     /* any FO_APOD_* ; 0 on unknown type */
+void fo_config_set_apodization(fo_config *cfg, const char *spec);     /* FLAC__stream_encoder_set_apodization */
 void fo_autocorrelation(const float *data, uint32_t data_len, uint32_t lag, double *autoc);
 void fo_lp_coefficients(const double *autoc, uint32_t *max_order, float lp_coeff[][FO_MAX_LPC_ORDER], double *error);
 uint32_t fo_best_order(const double *lpc_error, uint32_t max_order, uint32_t total_samples, uint32_t overhead_bits_per_order);

@@ -17,7 +17,7 @@ def ref_available():
     return reflib.available("default") and reflib.available("strict")
 
 
-def require_ref():
+def require_ref(variant=None):
     import reflib
     if not (reflib.available("default") and reflib.available("strict")):
         pytest.skip("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")

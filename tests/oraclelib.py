@@ -12,7 +12,7 @@ FO_MAX_PARTITIONS = 256
 
 
 class Apod(C.Structure):
-    _fields_ = [("type", C.c_int32), ("p", C.c_float), ("parts", C.c_int32)]
+    _fields_ = [("type", C.c_int32), ("p", C.c_float), ("parts", C.c_int32), ("start", C.c_float), ("end", C.c_float)]
 
 
 class Config(C.Structure):
@@ -79,6 +79,9 @@ def lib():
         L.fo_crc16.restype = C.c_uint16
         L.fo_crc16.argtypes = [C.c_void_p, C.c_size_t]
         L.fo_window_tukey.argtypes = [C.c_void_p, C.c_int32, C.c_float]
+        L.fo_config_set_apodization.argtypes = [C.POINTER(Config), C.c_char_p]
+        L.fo_window.restype = C.c_int
+        L.fo_window.argtypes = [C.POINTER(Apod), C.c_void_p, C.c_int32]
         L.fo_autocorrelation.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
@@ -88,8 +91,18 @@ def preset(channels, bps, rate, level, blocksize=0, **over):
     cfg = Config()
     lib().fo_config_preset(C.byref(cfg), channels, bps, rate, level, blocksize)
     for k, v in over.items():
-        setattr(cfg, k, v)
+        if k == "apodization":
+            lib().fo_config_set_apodization(C.byref(cfg), v.encode() if isinstance(v, str) else v)
+        else:
+            setattr(cfg, k, v)
     return cfg
+
+
+def window(apod, length):
+    out = np.empty(length, dtype=np.float32)
+    if not lib().fo_window(C.byref(apod), out.ctypes.data, length):
+        raise ValueError("unknown apodization type")
+    return out
 
 
 class Encoder:

@@ -68,7 +68,7 @@ class Sink:
         return 0
 
 
-def encode_with_api(x, bps, rate, level, chunk=2048, verify=False, planar=False, batch=None, md5=True):
+def encode_with_api(x, bps, rate, level, chunk=2048, verify=False, planar=False, batch=None, md5=True, apodization=None):
     lib = L()
     if batch:
         os.environ["FB200_BATCH_BLOCKS"] = str(batch)
@@ -77,6 +77,9 @@ def encode_with_api(x, bps, rate, level, chunk=2048, verify=False, planar=False,
     lib.FLAC__stream_encoder_set_bits_per_sample(e, C.c_uint32(bps))
     lib.FLAC__stream_encoder_set_sample_rate(e, C.c_uint32(rate))
     lib.FLAC__stream_encoder_set_compression_level(e, C.c_uint32(level))
+    if apodization is not None:  # after the level, like the flac CLI's -A
+        lib.FLAC__stream_encoder_set_apodization.argtypes = [C.c_void_p, C.c_char_p]
+        assert lib.FLAC__stream_encoder_set_apodization(e, apodization.encode())
     lib.FLAC__stream_encoder_set_verify(e, C.c_int(1 if verify else 0))
     lib.FLAC__stream_encoder_set_do_md5(e, C.c_int(1 if md5 else 0))
     sink = Sink()
