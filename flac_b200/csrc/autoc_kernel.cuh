@@ -1,0 +1,143 @@
+// autoc_kernel.cuh -- k_autoc3: windowed FP64 autocorrelation, one warp per 32 chains,
+// samples staged through shared memory with an asynchronous multi-stage copy pipeline.
+//
+// What bounds this kernel (tools/ubench/fp64_rates.cu, measured on B200): DFMA issues at
+// 64 lanes/clk/SM (2 cycles per warp instruction per SM sub-partition), a dependent DFMA takes
+// ~10.7 cycles, F2F.F64.F32 runs at 16 lanes/clk/SM on its own pipe.  A chain (one section of
+// one signal) must add its lag products in ascending sample order (lpc.c:121-140 sums that way
+// and every partial sum is rounded), so the only parallelism is ACROSS chains and across the
+// LAGS accumulators of one chain.  One thread therefore owns one chain with all its lags in
+// registers (LAGS independent DFMA chains >= the 6 needed to cover the DFMA latency), and the
+// job of the rest of the kernel is to keep that thread from ever waiting on memory: k_autoc2
+// (thread-private 128-bit global loads, one predicated window load per sample) spent ~230
+// cycles per sample against ~2*LAGS for the arithmetic, because with at most a few warps per
+// sub-partition nothing hides a load.
+//
+// Layout: CTA = one warp = 32 consecutive items of ONE section (so window indices, tile
+// counts and all control flow are warp-uniform).  Per tile of T samples the warp issues
+//   * 32 x T/4 16-byte cp.async.cg (each lane: consecutive 16-byte pieces of a row -> 128-byte
+//     coalesced segments) into rows of STRIDE words, STRIDE/4 odd => the 128-bit row reads of
+//     the 32 lanes (one row each) are bank-conflict free,
+//   * T 4-byte cp.async (zero-filled outside the section: the partial windows of
+//     lpc.c:82-94 become plain weights) for the window tile, read back as broadcast float4,
+// STAGES tiles deep.  The compute loop is branch-free: I2F, FMUL, F2F, LAGS x DFMA per sample.
+// fma(d, h, acc) equals the reference's acc += d*h exactly: d and h are floats widened to
+// double, so their product is exact in double and only the addition rounds.
+#pragma once
+
+#include "encode_kernels.cuh"
+
+namespace fb200 {
+
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+// 4-byte copy; src_bytes == 0 writes zeros without touching gmem
+__device__ __forceinline__ void cp_async_4_zfill(void *smem, const void *gmem, int src_bytes)
+{
+	const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// smallest row stride (words) >= T with stride % 4 == 0 and (stride / 4) odd
+__host__ __device__ constexpr int autoc3_stride(int T) { return ((T / 4) % 2 == 1) ? T : T + 4; }
+template <int LAGS, int U, int K, int STAGES>
+constexpr size_t autoc3_smem_bytes() { return (size_t)STAGES * (32 * autoc3_stride(U * K) + U * K) * 4; }
+
+template <int LAGS, int U, int K, int STAGES>
+__global__ void __launch_bounds__(32) k_autoc3(EncK P, const int32_t *__restrict__ sig, const SigMeta *__restrict__ meta,
+                                              const float *__restrict__ windows, const DevSection *__restrict__ secs,
+                                              double *__restrict__ autoc, int nitems)
+{
+	static_assert(U % LAGS == 0 && U % 4 == 0, "a body must be a whole number of history rotations and of 128-bit loads");
+	constexpr int T = U * K;
+	constexpr int STRIDE = autoc3_stride(T);
+	constexpr int STAGE_WORDS = 32 * STRIDE + T;
+	extern __shared__ int4 autoc3_smem[];
+	int *const smem = reinterpret_cast<int *>(autoc3_smem);
+
+	const int lane = threadIdx.x;
+	const int groups = (nitems + 31) >> 5;
+	const int sec = blockIdx.x / groups;
+	const int item0 = (blockIdx.x - sec * groups) << 5;
+	const int item = item0 + lane;
+	const bool live = item < nitems && meta[min(item, nitems - 1)].bps != 0;
+	if(!__any_sync(0xffffffffu, live)) return;
+
+	const DevSection S = secs[sec];
+	const float *w = windows + S.win_off;
+	const int shift = S.partial ? S.data_shift : 0;
+	const int a0 = shift & ~3;                                    // 16-byte aligned first sample fetched
+	const int nvalid = S.partial ? 2 * S.part_size : S.data_len;  // weights are 0 from here on (lpc.c:90-91): nothing to add
+	const int wsecond = P.bs - 2 * S.part_size;                   // window index offset of the falling half
+	const int ntiles = (shift - a0 + nvalid + T - 1) / T;
+
+	auto issue = [&](int t) {
+		if(t < ntiles) {
+			int *st = smem + (t % STAGES) * STAGE_WORDS;
+			const int32_t *g0 = sig + a0 + t * T;
+#pragma unroll
+			for(int j = 0; j < T / 4; j++) {
+				const int idx = j * 32 + lane;
+				const int row = idx / (T / 4), c = idx - row * (T / 4);
+				cp_async_16(st + row * STRIDE + c * 4, g0 + (size_t)min(item0 + row, nitems - 1) * P.bs_stride + c * 4);
+			}
+#pragma unroll
+			for(int j = 0; j < (T + 31) / 32; j++) {
+				const int u = j * 32 + lane;
+				if(u < T) {
+					const int i = a0 + t * T + u - shift;  // index inside the section
+					const bool ok = i >= 0 && i < nvalid;
+					const int wi = (!S.partial || i < S.part_size) ? i : wsecond + i;
+					cp_async_4_zfill(st + 32 * STRIDE + u, ok ? (w + wi) : w, ok ? 4 : 0);
+				}
+			}
+		}
+		cp_async_commit();  // one group per call, empty or not, keeps wait_group's count aligned with t
+	};
+
+	double acc[LAGS], h[LAGS];
+#pragma unroll
+	for(int l = 0; l < LAGS; l++) { acc[l] = 0.0; h[l] = 0.0; }
+
+#pragma unroll
+	for(int t = 0; t < STAGES - 1; t++) issue(t);
+	for(int t = 0; t < ntiles; t++) {
+		cp_async_wait<STAGES - 2>();  // tile t has landed (this lane's copies) ...
+		__syncwarp();                 // ... and every other lane's; all lanes are also done with tile t-1's buffer
+		issue(t + STAGES - 1);
+		const int *row = smem + (t % STAGES) * STAGE_WORDS + lane * STRIDE;
+		const float *win = reinterpret_cast<const float *>(smem + (t % STAGES) * STAGE_WORDS + 32 * STRIDE);
+#pragma unroll 1
+		for(int kb = 0; kb < K; kb++) {
+#pragma unroll
+			for(int q = 0; q < U / 4; q++) {
+				const int4 xq = *reinterpret_cast<const int4 *>(row + kb * U + q * 4);
+				const float4 wq = *reinterpret_cast<const float4 *>(win + kb * U + q * 4);
+				const int xs[4] = {xq.x, xq.y, xq.z, xq.w};
+				const float ws[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+				for(int e = 0; e < 4; e++) {
+					const int u = q * 4 + e;
+					const double dv = (double)__fmul_rn((float)xs[e], ws[e]);  // lpc.c:68-74: float product, widened
+					const int su = (LAGS - (u % LAGS)) % LAGS;                  // slot of the newest sample; slot (su+l)%LAGS holds d[i-l]
+					h[su] = dv;
+#pragma unroll
+					for(int l = 0; l < LAGS; l++) acc[l] = fma(dv, h[(su + l) % LAGS], acc[l]);
+				}
+			}
+		}
+	}
+	if(live) {
+		double *out = autoc + ((size_t)sec * nitems + item) * P.lag_stride;
+#pragma unroll
+		for(int l = 0; l < LAGS; l++) out[l] = acc[l];
+	}
+}
+
+}  // namespace fb200

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 		bool bad = false;
 		// tap class of this candidate: the rolled group loop below runs one small body per class
 		const int cls = wide ? (WIDEK ? ((MAXORD > 12 && order > 12) ? 5 : (MAXORD > 8 && order > 8) ? 4 : 3) : 6)
-		                     : ((MAXORD > 12 && order > 12) ? 2 : (MAXORD > 8 && order > 8) ? 1 : 0);
+		                     : ((MAXORD > 12 && order > 12) ? 2 : (MAXORD > 8 && order > 8) ? 1 : order > 4 ? 0 : 7);
 		constexpr int NT12 = MAXORD < 12 ? MAXORD : 12;
 		uint32_t s32 = 0;
 		unsigned long long s64 = 0;
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 	do {                                                                                                                   \
 		if(narrow) {                                                                                                       \
 			switch(cls) {                                                                                                  \
+				case 7: group_abs_sum<G, MAXORD, 4, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;         \
 				case 0: group_abs_sum<G, MAXORD, 8, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;         \
 				case 1: group_abs_sum<G, MAXORD, NT12, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;      \
 				case 2: group_abs_sum<G, MAXORD, MAXORD, false, MK, true>(xg, q, shift, ORD0, 0, s32, s64, bad); break;    \
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 		}                                                                                                                  \
 		else {                                                                                                             \
 			switch(cls) {                                                                                                  \
+				case 7: group_abs_sum<G, MAXORD, 4, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;        \
 				case 0: group_abs_sum<G, MAXORD, 8, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;        \
 				case 1: group_abs_sum<G, MAXORD, NT12, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;     \
 				case 2: group_abs_sum<G, MAXORD, MAXORD, false, MK, false>(xg, q, shift, ORD0, 0, s32, s64, bad); break;   \
@@ -295,11 +297,17 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 	if(bs > (int)kMaxFixedOrder) {
 		// fixed-predictor scan (fixed.c:222-290) + constant detection over all tiles
 		unsigned long long te[5] = {0, 0, 0, 0, 0};
-		uint32_t eq = 1;
+		uint32_t diff = 0;
 		const int32_t x0 = xs[0];
+		// The order-k error is the k-th finite difference; in wrapping 32-bit arithmetic it equals the
+		// reference's value whenever that fits an int32: |e4| <= 16 * 2^(sbps-1), i.e. sbps <= 27 (the
+		// engine's scope is sbps <= 25). |e| sums: a lane adds bs/32 values below 2^(sbps+3) per order, so
+		// 32-bit lane totals are exact when sbps + 3 + log2(bs/32) <= 32; otherwise they are flushed to
+		// 64 bits every 4 samples (4 * 2^28 < 2^32).
+		const bool lane_total_fits = (uint32_t)(sbps + 3) + ilog2_u32((uint32_t)(2 * (bs / 32) - 1)) <= 32u;
+		uint32_t t32[5] = {0, 0, 0, 0, 0};
 		for(int t = 0; t < ntiles; t++) {
 			const int row = t * 32 + lane;
-			const int base = row * R_T;
 			int xw[4 + R_T];
 			{
 				const int4 *pv = reinterpret_cast<const int4 *>(xs + row * 36);
@@ -311,20 +319,34 @@ __global__ void __launch_bounds__(NW * 32) k_search3(EncK P, const int32_t *__re
 					xw[4 + 4 * k] = v.x; xw[5 + 4 * k] = v.y; xw[6 + 4 * k] = v.z; xw[7 + 4 * k] = v.w;
 				}
 			}
+			// difference pyramid: e1[k] belongs to sample k-3, e2[k] to k-2, e3[k] to k-1, e4 to m
+			int e1[R_T + 3], e2[R_T + 2], e3[R_T + 1];
+#pragma unroll
+			for(int k = 0; k < R_T + 3; k++) e1[k] = xw[k + 1] - xw[k];
+#pragma unroll
+			for(int k = 0; k < R_T + 2; k++) e2[k] = e1[k + 1] - e1[k];
+#pragma unroll
+			for(int k = 0; k < R_T + 1; k++) e3[k] = e2[k + 1] - e2[k];
 #pragma unroll
 			for(int m = 0; m < R_T; m++) {
-				eq &= (xw[4 + m] == x0) ? 1u : 0u;
-				if(base + m >= (int)kMaxFixedOrder) {
-					const long long d0 = xw[4 + m], d1 = xw[3 + m], d2 = xw[2 + m], d3 = xw[1 + m], d4 = xw[m];
-					const long long e1 = d0 - d1, e2 = d0 - 2 * d1 + d2, e3 = d0 - 3 * d1 + 3 * d2 - d3, e4 = d0 - 4 * d1 + 6 * d2 - 4 * d3 + d4;
-					te[0] += (unsigned long long)(d0 < 0 ? -d0 : d0);
-					te[1] += (unsigned long long)(e1 < 0 ? -e1 : e1);
-					te[2] += (unsigned long long)(e2 < 0 ? -e2 : e2);
-					te[3] += (unsigned long long)(e3 < 0 ? -e3 : e3);
-					te[4] += (unsigned long long)(e4 < 0 ? -e4 : e4);
+				diff |= (uint32_t)(xw[4 + m] ^ x0);
+				const bool counted = m >= (int)kMaxFixedOrder || row != 0;  // fixed.c:222-290 starts at sample 4
+				if(counted) {
+					t32[0] = __sad(xw[4 + m], 0, t32[0]);
+					t32[1] = __sad(e1[m + 3], 0, t32[1]);
+					t32[2] = __sad(e2[m + 2], 0, t32[2]);
+					t32[3] = __sad(e3[m + 1], 0, t32[3]);
+					t32[4] = __sad(e3[m + 1] - e3[m], 0, t32[4]);
+				}
+				if((m & 3) == 3 && !lane_total_fits) {
+#pragma unroll
+					for(int k = 0; k < 5; k++) { te[k] += t32[k]; t32[k] = 0; }
 				}
 			}
 		}
+#pragma unroll
+		for(int k = 0; k < 5; k++) te[k] += t32[k];
+		uint32_t eq = diff == 0 ? 1u : 0u;
 #pragma unroll
 		for(int k = 0; k < 5; k++) te[k] = warp_sum_u64(te[k]);
 		eq = warp_and(eq);

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "encode_kernels_v3.cuh"
+#include "autoc_kernel.cuh"
 #include "windows.h"
 
 namespace fb200 {
@@ -85,6 +86,8 @@ struct fb200_encoder {
 	size_t h_totals_cap = 0;
 	uint64_t launches = 0;
 	bool autoc_split = false;
+	int pipe_chunks = 4;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS)
+	int autoc_version = 3;  // FB200_AUTOC_KERNEL=2 selects the thread-private-load generation (k_autoc2)
 	int search_version = 3;  // FB200_SEARCH_KERNEL=1|2|3 selects the search kernel generation (benchmarks/tests)
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
@@ -249,6 +252,13 @@ static void launch_autoc2(const EncK &k, const fb200_encoder *e, const Geometry 
 	k_autoc2<NACC, SPLIT, U><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
 }
 
+template <int LAGS, int U, int K, int STAGES>
+static void launch_autoc3(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
+{
+	const int groups = (nitems + 31) / 32;
+	k_autoc3<LAGS, U, K, STAGES><<<groups * k.nsec, 32, autoc3_smem_bytes<LAGS, U, K, STAGES>(), st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
+}
+
 template <int MO>
 static void launch_search2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
 {
@@ -321,7 +331,15 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 		else {
 			// one thread per chain (splitting the lags over two threads was measured slower: the sample
 			// stream conversion is paid twice); FB200_AUTOC_SPLIT=1 keeps the split variant selectable
-			if(e->autoc_split) {
+			if(e->autoc_version == 3) {
+				// warp per 32 chains, cp.async-staged tiles (autoc_kernel.cuh)
+				if(k.lags <= 7) launch_autoc3<7, 28, 2, 4>(k, e, g, nitems, st);
+				else if(k.lags <= 9) launch_autoc3<9, 36, 2, 4>(k, e, g, nitems, st);
+				else if(k.lags <= 13) launch_autoc3<13, 52, 1, 4>(k, e, g, nitems, st);
+				else if(k.lags <= 17) launch_autoc3<17, 68, 1, 3>(k, e, g, nitems, st);
+				else launch_autoc3<33, 132, 1, 3>(k, e, g, nitems, st);
+			}
+			else if(e->autoc_split) {
 				if(k.lags <= 7) launch_autoc2<4, 2, 8>(k, e, g, nitems, st);
 				else if(k.lags <= 9) launch_autoc2<5, 2, 20>(k, e, g, nitems, st);
 				else if(k.lags <= 13) launch_autoc2<7, 2, 28>(k, e, g, nitems, st);
@@ -656,6 +674,12 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 		e->use_v1 = env && env[0] == '1';
 		const char *as = getenv("FB200_AUTOC_SPLIT");
 		e->autoc_split = as && as[0] == '1';
+		const char *pc = getenv("FB200_PIPE_CHUNKS");
+		if(pc && atoi(pc) >= 1 && atoi(pc) <= 64) e->pipe_chunks = atoi(pc);
+		const char *av = getenv("FB200_AUTOC_KERNEL");
+		if(av && (av[0] == '2' || av[0] == '3')) e->autoc_version = av[0] - '0';
+		if(e->autoc_split) e->autoc_version = 2;
+		cudaFuncSetAttribute(k_autoc3<33, 132, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoc3_smem_bytes<33, 132, 1, 3>());
 		const char *sv = getenv("FB200_SEARCH_KERNEL");
 		if(sv && sv[0] >= '1' && sv[0] <= '3') e->search_version = sv[0] - '0';
 	}
@@ -716,7 +740,7 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 	unsigned long long *offs = reinterpret_cast<unsigned long long *>(d_frame_offsets);
 	if(samples == 0) FB_CUDA(cudaMemsetAsync(offs, 0, sizeof(unsigned long long), st));
 	// sub-batches: ~4 per call (at most max_blocks each) so that stage A of one overlaps stage B of the previous
-	uint64_t chunk = (nfull + 3) / 4;
+	uint64_t chunk = (nfull + e->pipe_chunks - 1) / e->pipe_chunks;
 	if(chunk < 512) chunk = 512;
 	if(chunk > e->max_blocks) chunk = e->max_blocks;
 	std::vector<PipeChunk> chunks;

@@ -161,7 +161,7 @@ def test_big_batch_property_round_trip():
 
 
 @pytest.mark.parametrize("env", [{"FB200_FORCE_GENERAL_KERNELS": "1"}, {"FB200_SEARCH_KERNEL": "2"}, {"FB200_SEARCH_KERNEL": "1"},
-                                 {"FB200_AUTOC_SPLIT": "1"}])
+                                 {"FB200_AUTOC_SPLIT": "1"}, {"FB200_AUTOC_KERNEL": "2"}])
 @pytest.mark.parametrize("level,ch,bps", [(8, 2, 16), (5, 2, 16), (8, 2, 24), (2, 1, 16)])
 def test_every_kernel_generation_is_bit_exact(env, level, ch, bps, monkeypatch):
     """The general kernels (any blocksize), the v2 CTA-per-signal search and the split autocorrelation are
