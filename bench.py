@@ -193,7 +193,7 @@ def bench_decode(args, rank, local_rank, world, dist, barrier, max_over_ranks, s
     if args.blocks:
         blocks = args.blocks
     x = make_pcm(ch, bps, rate, blocks, bs, seed=1 + rank)
-    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), device=local_rank, max_blocks_per_launch=int(os.environ.get("FB200_BENCH_MAXBLOCKS", "4096")))
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), device=local_rank, max_blocks_per_launch=4096)
     stream_np, offs_np = enc.encode(x)
     enc.close()
     total_bytes = int(offs_np[blocks])
@@ -405,7 +405,8 @@ def main():
     h_pcm.numpy()[:] = x
     d_pcm = h_pcm.to("cuda", non_blocking=False)
 
-    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), device=local_rank, max_blocks_per_launch=4096)
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), device=local_rank,
+                            max_blocks_per_launch=int(os.environ.get("FB200_BENCH_MAXBLOCKS", str(blocks))))
     out_cap = blocks * enc.max_frame_bytes + 64
     d_out = torch.empty(out_cap, dtype=torch.uint8, device="cuda")
     d_offs = torch.empty(blocks + 1, dtype=torch.int64, device="cuda")

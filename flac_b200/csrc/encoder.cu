@@ -16,6 +16,7 @@
 
 #include "encode_kernels_v3.cuh"
 #include "autoc_kernel.cuh"
+#include "search_kernel.cuh"
 #include "windows.h"
 
 namespace fb200 {
@@ -40,6 +41,7 @@ struct Geometry {
 	size_t search2_smem = 0, emit2_smem = 0;
 	int fast_search3 = 0;       // 0, or R_T (32/36) of the warp-per-signal kernel
 	size_t search3_smem = 0;
+	size_t search4_smem = 0;
 	int fast_search = 0, fast_emit = 0;  // 0 = general kernels; emit: 256 / 128 = CTA width of the fast kernel
 	int maxord_t = 8;
 };
@@ -86,9 +88,9 @@ struct fb200_encoder {
 	size_t h_totals_cap = 0;
 	uint64_t launches = 0;
 	bool autoc_split = false;
-	int pipe_chunks = 4;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS)
+	int pipe_chunks = 1;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS); see fb200_encode_device
 	int autoc_version = 3;  // FB200_AUTOC_KERNEL=2 selects the thread-private-load generation (k_autoc2)
-	int search_version = 3;  // FB200_SEARCH_KERNEL=1|2|3 selects the search kernel generation (benchmarks/tests)
+	int search_version = 4;  // FB200_SEARCH_KERNEL=1|2|3|4 selects the search kernel generation (benchmarks/tests)
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
 	bool prof_on = false;
@@ -225,9 +227,11 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 			if(bs % (32 * 32) == 0) rt = 32;
 			else if(bs % (32 * 36) == 0) rt = 36;
 			const size_t per_warp = rt ? (((size_t)(bs / rt) * 36 * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared) + 15) / 16 * 16) : 0;
-			if(rt && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * per_warp <= 110 * 1024) {
+			const int ntl = rt ? bs / (32 * rt) : 0;  // tiles; the partition <-> lane mapping needs a power of two
+			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * per_warp <= 110 * 1024) {
 				g.fast_search3 = rt;
 				g.search3_smem = 2 * per_warp;
+				g.search4_smem = 2 * search4_bytes_per_warp(bs, rt);
 			}
 		}
 		g.search2_smem = (size_t)xcap * 4;
@@ -282,6 +286,21 @@ static void launch_search3(const EncK &k, const fb200_encoder *e, const Geometry
 }
 
 template <int MO>
+static void launch_search4(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
+{
+	const int grid = (nitems + 1) / 2;
+	const bool widek = k.bps > 16;
+	if(g.fast_search3 == 32) {
+		if(widek) k_search4<32, MO, 2, true><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+		else k_search4<32, MO, 2, false><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+	}
+	else {
+		if(widek) k_search4<36, MO, 2, true><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+		else k_search4<36, MO, 2, false><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
+	}
+}
+
+template <int MO>
 static void launch_emit2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nb, cudaStream_t st)
 {
 	if(g.fast_emit == 256) {
@@ -298,6 +317,13 @@ static void set_smem_attrs(int search_bytes, int emit_bytes)
 	cudaFuncSetAttribute(k_search3<36, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 	cudaFuncSetAttribute(k_search3<32, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 	cudaFuncSetAttribute(k_search3<36, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	if(MO <= 12) {
+		constexpr int MO4 = MO <= 12 ? MO : 12;
+		cudaFuncSetAttribute(k_search4<32, MO4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+		cudaFuncSetAttribute(k_search4<36, MO4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+		cudaFuncSetAttribute(k_search4<32, MO4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+		cudaFuncSetAttribute(k_search4<36, MO4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	}
 	cudaFuncSetAttribute(k_search2<32, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
 	cudaFuncSetAttribute(k_search2<36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
 	cudaFuncSetAttribute(k_emit2<256, 16, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
@@ -372,7 +398,14 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, int nb, uint32_t first_fra
 	k.first_frame = first_frame;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
-	if(g.fast_search3 && !e->use_v1 && e->search_version >= 3) {
+	if(g.fast_search3 && !e->use_v1 && e->search_version >= 4) {
+		// orders above 12 (non-preset -l 13..32) stay on k_search3: k_search4's 32-tap instantiation mis-evaluates
+		// orders > 16 (found by tests/test_gpu_encode.py::test_option_matrix; not yet root-caused)
+		if(g.maxord_t == 8) launch_search4<8>(k, e, g, nitems, st);
+		else if(g.maxord_t == 12) launch_search4<12>(k, e, g, nitems, st);
+		else launch_search3<32>(k, e, g, nitems, st);
+	}
+	else if(g.fast_search3 && !e->use_v1 && e->search_version >= 3) {
 		if(g.maxord_t == 8) launch_search3<8>(k, e, g, nitems, st);
 		else if(g.maxord_t == 12) launch_search3<12>(k, e, g, nitems, st);
 		else launch_search3<32>(k, e, g, nitems, st);
@@ -681,7 +714,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 		if(e->autoc_split) e->autoc_version = 2;
 		cudaFuncSetAttribute(k_autoc3<33, 132, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoc3_smem_bytes<33, 132, 1, 3>());
 		const char *sv = getenv("FB200_SEARCH_KERNEL");
-		if(sv && sv[0] >= '1' && sv[0] <= '3') e->search_version = sv[0] - '0';
+		if(sv && sv[0] >= '1' && sv[0] <= '4') e->search_version = sv[0] - '0';
 	}
 	*out = e;
 	return FB200_OK;
@@ -739,7 +772,10 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
 	unsigned long long *offs = reinterpret_cast<unsigned long long *>(d_frame_offsets);
 	if(samples == 0) FB_CUDA(cudaMemsetAsync(offs, 0, sizeof(unsigned long long), st));
-	// sub-batches: ~4 per call (at most max_blocks each) so that stage A of one overlaps stage B of the previous
+	// Sub-batches of at most max_blocks blocks; stage A (prep/autoc/lpc) of one overlaps stage B (search/emit) of the
+	// previous on a second stream. Measured (tools/sweep_chunks.sh, 10 000 blocks): one launch set per call is fastest
+	// (-5: 1.85 ms vs 2.02 ms with 4 sub-batches; -8: 4.62 vs 4.87) -- every kernel is more efficient at full batch
+	// size than the overlap wins back, so the default is as few sub-batches as the workspace allows.
 	uint64_t chunk = (nfull + e->pipe_chunks - 1) / e->pipe_chunks;
 	if(chunk < 512) chunk = 512;
 	if(chunk > e->max_blocks) chunk = e->max_blocks;

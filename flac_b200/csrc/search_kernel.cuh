@@ -1,0 +1,411 @@
+// search_kernel.cuh -- k_search4: one warp per (block, signal), register-resident partition tree.
+//
+// ncu on k_search3 at -8 (profiles/r1c_*): the FIR taps were 37 % of the instructions but only
+// 28 % of the time; 40 % went into the per-candidate tail (zeroing / read-modify-write of a
+// shared-memory heap, six barrier-separated merge levels, four chunked parameter sweeps with
+// 64-bit shared traffic) and 19 % into group-loop control (a jump-table switch and ~50
+// address instructions per 16-output group).  This generation keeps the arithmetic and the
+// decision order (stream_encoder.c:4191-4269, 4701-5075) and changes the mechanics:
+//   * the predictor class (taps x width) is chosen ONCE per candidate; the tile/group loops are
+//     straight pointer walks (a zeroed row in front of the signal removes the row-0 branch);
+//   * a run's |residual| sum goes to its leaf with a plain store (no zeroing, no RMW, no barrier);
+//   * the partition tree lives in registers: a lane owns 2^(max_po-5) consecutive leaves, merges
+//     them locally down to order 5 and continues with xor-shuffles; Rice parameter and bit count
+//     of a node are computed where the node lives; an order's total is one warp reduction;
+//     the best order is tracked in registers while walking the orders downwards.
+#pragma once
+
+#include "encode_kernels_v3.cuh"
+
+namespace fb200 {
+
+struct SearchWarpShared4 {
+	unsigned long long leaf[kMaxPartitions];  // |residual| sums of the finest partitions of the candidate in flight
+	uint8_t params_all[2 * kMaxPartitions];   // heap: node n = (1 << po) + p
+	uint8_t b_params[kMaxPartitions];         // parameters of the best candidate so far
+};
+
+constexpr int kSearch4ZeroRow = 36;  // words of zeros in front of a warp's signal slice
+
+__host__ __device__ constexpr size_t search4_bytes_per_warp(int bs, int R_T)
+{
+	return ((size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared4) + 15) / 16 * 16;
+}
+
+// All runs of one candidate: leaf[p] = sum of |residual| over finest partition p.
+// xs = first sample of the warp's slice (row stride 36 words, kSearch4ZeroRow zero words in front).
+// lpp_log: log2(lanes per partition) when a partition fits in a tile (tpp == 1), else tpp tiles make one partition.
+// Returns true when a wide residual left the int32 range (lpc.c:868-884).
+template <int R_T, int MAXORD, int NTAPS, bool WIDE, bool NARROW>
+__device__ __forceinline__ bool fir_partition_sums(const int32_t *xs, const int (&q)[MAXORD], int shift, int order, int limit,
+                                                   int ntiles, int lane, int lpp_log, int tpp, bool mask32, unsigned long long *leaf)
+{
+	constexpr int G = (R_T == 32) ? 16 : 12, NG = R_T / G, ROWPAD = 36 - R_T;
+	bool bad = false;
+	unsigned long long carry = 0;
+#pragma unroll 1
+	for(int t = 0; t < ntiles; t++) {
+		const int32_t *rowp = xs + (t * 32 + lane) * 36;
+		uint32_t s32 = 0;
+		unsigned long long s64 = 0;
+#pragma unroll 1
+		for(int g = 0; g < NG; g++) {
+			int xg[MAXORD + G];
+			const int32_t *op = rowp + g * G;                               // first output of the group
+			// history vector k holds samples [g*G - MAXORD + 4k, +4) of the run; negative ones live in the previous row,
+			// i.e. behind the row pad (MAXORD <= R_T, so never further than one row back)
+#pragma unroll
+			for(int k = 0; k < MAXORD / 4; k++) {
+				const int4 v = *reinterpret_cast<const int4 *>(op - MAXORD + 4 * k - ((g * G + 4 * k < MAXORD) ? ROWPAD : 0));
+				xg[4 * k] = v.x; xg[4 * k + 1] = v.y; xg[4 * k + 2] = v.z; xg[4 * k + 3] = v.w;
+			}
+#pragma unroll
+			for(int k = 0; k < G / 4; k++) {
+				const int4 v = *reinterpret_cast<const int4 *>(op + 4 * k);
+				xg[MAXORD + 4 * k] = v.x; xg[MAXORD + 4 * k + 1] = v.y; xg[MAXORD + 4 * k + 2] = v.z; xg[MAXORD + 4 * k + 3] = v.w;
+			}
+			if(t == 0) {
+				// warm-up samples of the block (the first `order` outputs of row 0) are not residuals
+				const int ord_g = lane == 0 ? order - g * G : 0;
+				group_abs_sum<G, MAXORD, NTAPS, WIDE, true, NARROW>(xg, q, shift, ord_g, limit, s32, s64, bad);
+			}
+			else group_abs_sum<G, MAXORD, NTAPS, WIDE, false, NARROW>(xg, q, shift, 0, limit, s32, s64, bad);
+		}
+		if(tpp == 1) {
+			const int lpp = 1 << lpp_log;
+			if(NARROW) {
+				uint32_t s = s32;  // the reference's 32-bit accumulator wraps (stream_encoder.c:4815-4824); so does this
+				for(int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+				if((lane & (lpp - 1)) == 0) leaf[(t * 32 + lane) >> lpp_log] = s;
+			}
+			else {
+				unsigned long long s = s64;
+				for(int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+				if((lane & (lpp - 1)) == 0) leaf[(t * 32 + lane) >> lpp_log] = mask32 ? (unsigned long long)(uint32_t)s : s;
+			}
+		}
+		else {
+			carry += warp_sum_u64(NARROW ? (unsigned long long)s32 : s64);
+			if((t + 1) % tpp == 0) {
+				if(lane == 0) leaf[t / tpp] = (NARROW || mask32) ? (unsigned long long)(uint32_t)carry : carry;
+				carry = 0;
+			}
+		}
+	}
+	return bad;
+}
+
+template <int R_T, int MAXORD, int NW, bool WIDEK>
+__global__ void __launch_bounds__(NW * 32) k_search4(EncK P, const int32_t *__restrict__ sig, const SigMeta *__restrict__ meta,
+                                                    const CandDesc *__restrict__ cdesc, SubframePlan *__restrict__ plans, int nitems)
+{
+	static_assert(MAXORD >= 8 && MAXORD % 4 == 0 && R_T % 4 == 0 && MAXORD + 4 <= kSearch4ZeroRow, "vector loads / zero row");
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, bs = P.bs;
+	const int item = blockIdx.x * NW + warp;
+	if(item >= nitems) return;
+	const int nrows = bs / R_T;
+	const size_t xs_bytes = ((size_t)(kSearch4ZeroRow + nrows * 36) * 4 + 15) / 16 * 16;
+	const size_t per_warp = xs_bytes + (sizeof(SearchWarpShared4) + 15) / 16 * 16;
+	int32_t *xs = reinterpret_cast<int32_t *>(smem_raw + per_warp * warp) + kSearch4ZeroRow;
+	SearchWarpShared4 &S = *reinterpret_cast<SearchWarpShared4 *>(smem_raw + per_warp * warp + xs_bytes);
+
+	const SigMeta M = meta[item];
+	SubframePlan *plan = plans + item;
+	if(M.bps == 0) {
+		if(lane == 0) { plan->type = -1; plan->est_bits = 0xffffffffu; }
+		return;
+	}
+	const int sbps = M.bps, wasted = M.wasted;
+	{
+		const int32_t *g = sig + (size_t)item * P.bs_stride;
+		for(int i = lane; i < kSearch4ZeroRow; i += 32) xs[i - kSearch4ZeroRow] = 0;
+		if(R_T == 32) {
+			// 128-bit global loads, 128-bit shared stores: vector j of the block goes to row j/8, slot j%8
+			for(int j = lane; j < bs / 4; j += 32)
+				*reinterpret_cast<int4 *>(xs + (j >> 3) * 36 + (j & 7) * 4) = __ldg(reinterpret_cast<const int4 *>(g) + j);
+		}
+		else {
+			for(int j = lane; j < bs / 4; j += 32) *reinterpret_cast<int4 *>(xs + 4 * j) = __ldg(reinterpret_cast<const int4 *>(g) + j);
+		}
+		for(int p = lane; p < kMaxPartitions; p += 32) S.b_params[p] = 0;
+	}
+	__syncwarp();
+
+	constexpr int TILE = 32 * R_T;
+	constexpr int GAPV = (R_T == 32 ? 4 : 0) / 4;  // pad int4s between a row's history and its start
+	const int ntiles = bs / TILE;
+
+	// best-so-far (uniform across the warp)
+	uint32_t best_bits;
+	int b_type = SF_VERBATIM, b_order = 0, b_prec = 0, b_shift = 0, b_method = 0, b_po = 0, b_wide = 0;
+	int b_q[MAXORD];
+#pragma unroll
+	for(int j = 0; j < MAXORD; j++) b_q[j] = 0;
+	if(P.dis_verb && bs >= (int)kMaxFixedOrder) best_bits = 0xffffffffu;
+	else best_bits = kSubframeHeaderBits + (uint32_t)wasted + (uint32_t)bs * (uint32_t)sbps;
+
+	auto evaluate = [&](int type, int order, int precision, int shift, int wide, int limit, const int (&q)[MAXORD]) {
+		int max_po = P.max_po;
+		while(max_po > 0 && (bs >> max_po) <= order) max_po--;
+		const int min_po = min(P.min_po, max_po);
+		const int psize = bs >> max_po;
+		const bool narrow = (uint32_t)(sbps + (int)kMaxExtraResidualBps) < 32u - ilog2_u32((uint32_t)psize);
+		const int tpp = psize > TILE ? psize / TILE : 1;
+		const int lpp_log = tpp == 1 ? (int)ilog2_u32((uint32_t)(psize / R_T)) : 5;
+
+		// ---- residual pass, one predictor class per candidate
+		constexpr int NT12 = MAXORD < 12 ? MAXORD : 12;
+		bool bad = false;
+		if(!wide && narrow) {
+			if(order <= 4) bad = fir_partition_sums<R_T, MAXORD, 4, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, S.leaf);
+			else if(order <= 8) bad = fir_partition_sums<R_T, MAXORD, 8, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, S.leaf);
+			else if(MAXORD > 8 && order <= 12) bad = fir_partition_sums<R_T, MAXORD, NT12, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, S.leaf);
+			else bad = fir_partition_sums<R_T, MAXORD, MAXORD, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, S.leaf);
+		}
+		else if(!wide) {
+			if(order <= 8) bad = fir_partition_sums<R_T, MAXORD, 8, false, false>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+			else if(MAXORD > 8 && order <= 12) bad = fir_partition_sums<R_T, MAXORD, NT12, false, false>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+			else bad = fir_partition_sums<R_T, MAXORD, MAXORD, false, false>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+		}
+		else if(WIDEK) {
+			if(order <= 8) bad = fir_partition_sums<R_T, MAXORD, 8, true, false>(xs, q, shift, order, limit, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+			else if(MAXORD > 8 && order <= 12) bad = fir_partition_sums<R_T, MAXORD, NT12, true, false>(xs, q, shift, order, limit, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+			else bad = fir_partition_sums<R_T, MAXORD, MAXORD, true, false>(xs, q, shift, order, limit, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+		}
+		else bad = fir_partition_sums<R_T, MAXORD, MAXORD, true, false>(xs, q, shift, order, limit, ntiles, lane, lpp_log, tpp, narrow, S.leaf);
+		if(__any_sync(0xffffffffu, bad)) return;  // evaluate_lpc_subframe_ returns 0 (stream_encoder.c:4601-4609)
+		__syncwarp();
+
+		// ---- partition orders max_po .. min_po (find_best_partition_order_, :4701-4795; set_partitioned_rice_, :4954-5075)
+		uint32_t best_r = 0;
+		int best_po = 0;
+		const uint32_t rice_cap = (uint32_t)P.rice_limit - 1;
+		// Rice parameter (:4994-5010) + bit count (:4929-4951) of heap node n holding `mean`; stores the parameter when `own`
+		auto node_bits = [&](unsigned long long mean, uint32_t psamp, uint32_t div, int n, bool own) -> uint32_t {
+			uint32_t k;
+			if((mean >> 32) == 0) {
+				// ((mean - 1) * div) >> 18 in 32-bit pieces: div <= 2^18, so the product is below 2^50 and the result below 2^32
+				const uint32_t m32 = (uint32_t)mean;
+				const uint32_t m1 = m32 - 1;
+				const uint32_t t = m32 < 2 ? 0u : __funnelshift_r(m1 * div, __umulhi(m1, div), 18);
+				k = t ? 32u - (uint32_t)__clz((int)t) : 0u;
+			}
+			else {
+				const unsigned long long t = ((mean - 1) * div) >> 18;
+				k = t ? ilog2_u64(t) + 1 : 0u;
+			}
+			if(k > rice_cap) k = rice_cap;
+			if(own) S.params_all[n] = (uint8_t)k;
+			return own ? count_rice_bits(k, psamp, mean) : 0u;
+		};
+		auto close_order = [&](int po, unsigned long long lane_bits) {
+			unsigned long long total;
+			if(__any_sync(0xffffffffu, (lane_bits >> 27) != 0)) total = warp_sum_u64(lane_bits);
+			else total = __reduce_add_sync(0xffffffffu, (unsigned)lane_bits);  // 32 lanes x 2^27 cannot wrap
+			total += kEntropyTypeLen + kRiceOrderLen;
+			const uint32_t bits = (uint32_t)(total < 0xffffffffull ? total : 0xffffffffull);
+			if(best_r == 0 || bits < best_r) { best_r = bits; best_po = po; }
+		};
+		// orders >= 5: a lane owns 2^(po-5) consecutive nodes, merged in registers on the way down
+		unsigned long long cur;  // after this block: the node of order `lev` this lane's group of 32 >> lev lanes stands for
+		int lev;
+		if(max_po >= 5) {
+			unsigned long long v[8];
+			const int cnt0 = 1 << (max_po - 5);
+#pragma unroll
+			for(int i = 0; i < 8; i++) v[i] = i < cnt0 ? S.leaf[lane * cnt0 + i] : 0ull;
+			int po = max_po;
+#pragma unroll 1
+			for(; po >= 5 && po >= min_po; po--) {
+				const int cnt = 1 << (po - 5);
+				const uint32_t pbase = (uint32_t)(bs >> po);
+				const uint32_t div_rest = 0x40000u / pbase, div_first = 0x40000u / (pbase - (uint32_t)order);
+				unsigned long long b = 0;
+#pragma unroll
+				for(int i = 0; i < 8; i++)
+					if(i < cnt) {
+						const int p = lane * cnt + i;
+						b += node_bits(v[i], p == 0 ? pbase - (uint32_t)order : pbase, p == 0 ? div_first : div_rest, (1 << po) + p, true);
+					}
+				close_order(po, b);
+#pragma unroll
+				for(int i = 0; i < 4; i++)
+					if(2 * i + 1 < cnt) v[i] = v[2 * i] + v[2 * i + 1];
+			}
+			cur = v[0];
+			lev = 5;
+		}
+		else {
+			cur = S.leaf[lane >> (5 - max_po)];
+			lev = max_po;
+		}
+		// orders <= 4 (31 nodes): heap node n = (1 << L) + p is evaluated once, by lane n - 1. Walking down, every lane of a
+		// node's group holds the node's sum; the evaluating lane fetches it from the group's first lane.
+		if(min_po <= 4) {
+			const int n1 = lane + 1;
+			const int myL = (int)ilog2_u32((uint32_t)n1);
+			const int myP = n1 - (1 << myL);
+			unsigned long long mine = 0;
+#pragma unroll
+			for(int L = 4; L >= 0; L--) {
+				if(L < lev) cur += __shfl_xor_sync(0xffffffffu, cur, 16 >> L);  // two order-(L+1) groups make one order-L group
+				const unsigned long long got = __shfl_sync(0xffffffffu, cur, (myP << (5 - L)) & 31);
+				if(myL == L) mine = got;
+			}
+			const int top = max_po < 4 ? max_po : 4;
+			const bool active = lane < 31 && myL >= min_po && myL <= top;
+			const uint32_t psamp = (uint32_t)(bs >> myL) - (myP == 0 ? (uint32_t)order : 0u);
+			const uint32_t bits = node_bits(mine, psamp, 0x40000u / psamp, n1, active);
+#pragma unroll
+			for(int L = 4; L >= 0; L--)
+				if(L <= top && L >= min_po) close_order(L, (active && myL == L) ? bits : 0u);
+		}
+
+		uint32_t estimate = kSubframeHeaderBits + (uint32_t)wasted;
+		if(type == SF_FIXED) estimate += (uint32_t)order * (uint32_t)sbps;
+		else estimate += kQlpPrecisionLen + kQlpShiftLen + (uint32_t)order * (uint32_t)(precision + sbps);
+		if(best_r < 0xffffffffu - estimate) estimate += best_r;
+		else estimate = 0xffffffffu;
+		const bool better = (type == SF_LPC ? estimate > 0 : true) && estimate < best_bits;
+		if(better) {
+			__syncwarp();  // params_all was written by the lanes that own the nodes
+			uint32_t any15 = 0;
+			for(int p = lane; p < (1 << best_po); p += 32) {
+				const uint8_t k = S.params_all[(1 << best_po) + p];
+				S.b_params[p] = k;
+				any15 |= (k >= kRiceEscape) ? 1u : 0u;
+			}
+			any15 = warp_or(any15);
+			best_bits = estimate;
+			b_type = type; b_order = order; b_prec = precision; b_shift = shift; b_method = any15 ? 1 : 0; b_po = best_po; b_wide = wide;
+#pragma unroll
+			for(int j = 0; j < MAXORD; j++) b_q[j] = (type == SF_LPC) ? q[j] : 0;
+		}
+		__syncwarp();
+	};
+
+	if(bs > (int)kMaxFixedOrder) {
+		// fixed-predictor scan (fixed.c:222-290) + constant detection over all tiles
+		unsigned long long te[5] = {0, 0, 0, 0, 0};
+		uint32_t diff = 0;
+		const int32_t x0 = xs[0];
+		// The order-k error is the k-th finite difference; in wrapping 32-bit arithmetic it equals the
+		// reference's value whenever that fits an int32: |e4| <= 16 * 2^(sbps-1), i.e. sbps <= 27 (the
+		// engine's scope is sbps <= 25). |e| sums: a lane adds bs/32 values below 2^(sbps+3) per order, so
+		// 32-bit lane totals are exact when sbps + 3 + log2(bs/32) <= 32; otherwise they are flushed to
+		// 64 bits every 4 samples (4 * 2^28 < 2^32).
+		const bool lane_total_fits = (uint32_t)(sbps + 3) + ilog2_u32((uint32_t)(2 * (bs / 32) - 1)) <= 32u;
+		uint32_t t32[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+		for(int t = 0; t < ntiles; t++) {
+			const int row = t * 32 + lane;
+			int xw[4 + R_T];
+			{
+				const int4 *pv = reinterpret_cast<const int4 *>(xs + row * 36);
+				const int4 hv = pv[-1 - GAPV];  // row 0 reads the zero row
+				xw[0] = hv.x; xw[1] = hv.y; xw[2] = hv.z; xw[3] = hv.w;
+#pragma unroll
+				for(int k = 0; k < R_T / 4; k++) {
+					const int4 v = pv[k];
+					xw[4 + 4 * k] = v.x; xw[5 + 4 * k] = v.y; xw[6 + 4 * k] = v.z; xw[7 + 4 * k] = v.w;
+				}
+			}
+			// difference pyramid: e1[k] belongs to sample k-3, e2[k] to k-2, e3[k] to k-1, e4 to m
+			int e1[R_T + 3], e2[R_T + 2], e3[R_T + 1];
+#pragma unroll
+			for(int k = 0; k < R_T + 3; k++) e1[k] = xw[k + 1] - xw[k];
+#pragma unroll
+			for(int k = 0; k < R_T + 2; k++) e2[k] = e1[k + 1] - e1[k];
+#pragma unroll
+			for(int k = 0; k < R_T + 1; k++) e3[k] = e2[k + 1] - e2[k];
+#pragma unroll
+			for(int m = 0; m < R_T; m++) {
+				diff |= (uint32_t)(xw[4 + m] ^ x0);
+				const bool counted = m >= (int)kMaxFixedOrder || row != 0;  // fixed.c:222-290 starts at sample 4
+				if(counted) {
+					t32[0] = __sad(xw[4 + m], 0, t32[0]);
+					t32[1] = __sad(e1[m + 3], 0, t32[1]);
+					t32[2] = __sad(e2[m + 2], 0, t32[2]);
+					t32[3] = __sad(e3[m + 1], 0, t32[3]);
+					t32[4] = __sad(e3[m + 1] - e3[m], 0, t32[4]);
+				}
+				if((m & 3) == 3 && !lane_total_fits) {
+#pragma unroll
+					for(int k = 0; k < 5; k++) { te[k] += t32[k]; t32[k] = 0; }
+				}
+			}
+		}
+#pragma unroll
+		for(int k = 0; k < 5; k++) te[k] += t32[k];
+		uint32_t eq = diff == 0 ? 1u : 0u;
+#pragma unroll
+		for(int k = 0; k < 5; k++) te[k] = warp_sum_u64(te[k]);
+		eq = warp_and(eq);
+		int guess;
+		{
+			const unsigned long long m34 = te[3] < te[4] ? te[3] : te[4], m234 = te[2] < m34 ? te[2] : m34, m1234 = te[1] < m234 ? te[1] : m234;
+			if(te[0] <= m1234) guess = 0;
+			else if(te[1] <= m234) guess = 1;
+			else if(te[2] <= m34) guess = 2;
+			else if(te[3] <= te[4]) guess = 3;
+			else guess = 4;
+		}
+		float rbps[5];
+		{
+			// one lane per order evaluates the log (fixed.c:284-288); the results are broadcast
+			const double n = (double)(uint32_t)(bs - (int)kMaxFixedOrder);
+			unsigned long long mine = te[0];
+#pragma unroll
+			for(int k = 1; k < 5; k++) mine = lane == k ? te[k] : mine;
+			const float r = (float)((mine > 0) ? fb_log(M_LN2 * (double)mine / n) / M_LN2 : 0.0);
+#pragma unroll
+			for(int k = 0; k < 5; k++) rbps[k] = __shfl_sync(0xffffffffu, r, k);
+		}
+		const bool is_constant = !P.dis_const && rbps[1] == 0.0f && eq;
+		if(is_constant) {
+			const uint32_t cbits = kSubframeHeaderBits + (uint32_t)wasted + (uint32_t)sbps;
+			if(cbits < best_bits) { best_bits = cbits; b_type = SF_CONSTANT; }
+		}
+		else {
+			if(!P.dis_fixed || (P.max_order == 0 && best_bits == 0xffffffffu)) {
+				int lo, hi;
+				if(P.exhaustive) { lo = 0; hi = (int)kMaxFixedOrder; }
+				else lo = hi = guess;
+				if(hi >= bs) hi = bs - 1;
+				for(int fo = lo; fo <= hi; fo++) {
+					if(rbps[fo] >= (float)sbps) continue;
+					int q[MAXORD];
+#pragma unroll
+					for(int j = 0; j < MAXORD; j++) q[j] = fixed_tap(fo, j);
+					evaluate(SF_FIXED, fo, 0, 0, 0, 0, q);
+				}
+			}
+			if(P.max_order > 0) {
+				const CandDesc *cd = cdesc + (size_t)item * P.nslots;
+				for(int c = 0; c < P.nslots; c++) {
+					const CandDesc *D = cd + c;
+					if(!D->valid) continue;
+					int q[MAXORD];
+#pragma unroll
+					for(int j = 0; j < MAXORD; j++) q[j] = __ldg(&D->qlp[j]);
+					evaluate(SF_LPC, D->order, D->precision, D->shift, D->wide, D->limit, q);
+				}
+			}
+		}
+	}
+	if(best_bits == 0xffffffffu) {
+		b_type = SF_VERBATIM;
+		best_bits = kSubframeHeaderBits + (uint32_t)wasted + (uint32_t)bs * (uint32_t)sbps;
+	}
+	if(lane == 0) {
+		plan->type = b_type; plan->order = b_order; plan->wasted = wasted; plan->bps = sbps;
+		plan->precision = b_prec; plan->shift = b_shift; plan->method = b_method; plan->porder = b_po;
+		plan->est_bits = best_bits; plan->wide = b_wide;
+#pragma unroll
+		for(int j = 0; j < FB200_MAX_LPC_ORDER; j++) plan->qlp[j] = (j < MAXORD) ? b_q[j < MAXORD ? j : 0] : 0;
+	}
+	for(int p = lane; p < kMaxPartitions; p += 32) plan->params[p] = S.b_params[p];
+}
+
+}  // namespace fb200

@@ -54,7 +54,7 @@ def test_depths_and_channel_counts(level, ch, bps, rate):
         _assert_same(got, ref, "reference[default]")
 
 
-@pytest.mark.parametrize("bs", [16, 17, 32, 33, 192, 256, 576, 1000, 1152, 2304, 4608, 8192])
+@pytest.mark.parametrize("bs", [16, 17, 32, 33, 192, 256, 576, 1000, 1024, 1152, 2048, 2304, 3072, 4608, 5120, 6144, 8192, 9216])
 @pytest.mark.parametrize("level", [2, 5, 8])
 def test_blocksizes(bs, level):
     x = signals.music_like(max(3 * bs + bs // 3, 600), 2, 16, 44100, seed=3)
@@ -160,7 +160,7 @@ def test_big_batch_property_round_trip():
     enc.close()
 
 
-@pytest.mark.parametrize("env", [{"FB200_FORCE_GENERAL_KERNELS": "1"}, {"FB200_SEARCH_KERNEL": "2"}, {"FB200_SEARCH_KERNEL": "1"},
+@pytest.mark.parametrize("env", [{"FB200_FORCE_GENERAL_KERNELS": "1"}, {"FB200_SEARCH_KERNEL": "3"}, {"FB200_SEARCH_KERNEL": "2"}, {"FB200_SEARCH_KERNEL": "1"},
                                  {"FB200_AUTOC_SPLIT": "1"}, {"FB200_AUTOC_KERNEL": "2"}])
 @pytest.mark.parametrize("level,ch,bps", [(8, 2, 16), (5, 2, 16), (8, 2, 24), (2, 1, 16)])
 def test_every_kernel_generation_is_bit_exact(env, level, ch, bps, monkeypatch):
