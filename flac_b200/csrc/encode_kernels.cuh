@@ -790,6 +790,10 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b)
 	return r;
 }
 
+// x^(2^j) mod (x^16+x^15+x^2+1) for j = 0..14 (x has order 32767, so x^(2^15) = x and the table is periodic);
+// generated with gf16_mul by repeated squaring from x = 0x2.
+__device__ __constant__ const uint16_t kCrcXPow2[15] = {0x2, 0x4, 0x10, 0x100, 0x8005, 0x8017, 0x8113, 0x106, 0x8011, 0x8107, 0x16, 0x114, 0x8115, 0x112, 0x8101};
+
 // block-wide exclusive scan for 256 threads; returns exclusive prefix, *total = sum
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*[9]*/, uint32_t *total)
 {

@@ -554,30 +554,52 @@ __global__ void __launch_bounds__(NT) k_emit2(EncK P, const int32_t *__restrict_
 		const int32_t *g = sig + ((size_t)blk * P.nsig + sidx) * P.bs_stride;
 		const uint32_t hdr_bits = kSubframeHeaderBits + (uint32_t)wasted;
 
-		if(tid == 0) {
+		// Subframe header (frame-format: type byte, wasted-bits unary, warm-up samples, precision/shift, coefficients,
+		// entropy method + partition order): every field's bit position is known, so each goes out from its own thread.
+		{
+			const uint32_t warm0 = bitpos + hdr_bits;                              // first warm-up sample
+			const uint32_t after_warm = warm0 + (uint32_t)order * (uint32_t)sbps;  // precision (LPC) or entropy method (fixed)
+			const bool predicted = type == SF_FIXED || type == SF_LPC;
 			BitPut bw;
-			bw.init(words, bitpos);
-			uint32_t tb;
-			switch(type) {
-				case SF_CONSTANT: tb = 0x00; break;
-				case SF_VERBATIM: tb = 0x02; break;
-				case SF_FIXED: tb = 0x10 | ((uint32_t)order << 1); break;
-				default: tb = 0x40 | ((uint32_t)(order - 1) << 1); break;
+			if(tid == 0) {
+				uint32_t tb;
+				switch(type) {
+					case SF_CONSTANT: tb = 0x00; break;
+					case SF_VERBATIM: tb = 0x02; break;
+					case SF_FIXED: tb = 0x10 | ((uint32_t)order << 1); break;
+					default: tb = 0x40 | ((uint32_t)(order - 1) << 1); break;
+				}
+				bw.init(words, bitpos);
+				bw.put(tb | (wasted ? 1u : 0u), 8);
+				if(wasted) { bw.skip((uint32_t)wasted - 1); bw.put(1, 1); }
+				if(type == SF_CONSTANT) bw.put(mask_bits(g[0], (uint32_t)sbps), (uint32_t)sbps);
+				bw.finish();
 			}
-			bw.put(tb | (wasted ? 1u : 0u), 8);
-			if(wasted) { bw.skip((uint32_t)wasted - 1); bw.put(1, 1); }
-			if(type == SF_CONSTANT) bw.put(mask_bits(g[0], (uint32_t)sbps), (uint32_t)sbps);
-			else if(type == SF_FIXED || type == SF_LPC) {
-				for(int i = 0; i < order; i++) bw.put(mask_bits(g[i], (uint32_t)sbps), (uint32_t)sbps);
+			else if(predicted && tid >= 32 && tid < 32 + order) {
+				const int i = tid - 32;
+				bw.init(words, warm0 + (uint32_t)i * (uint32_t)sbps);
+				bw.put(mask_bits(g[i], (uint32_t)sbps), (uint32_t)sbps);
+				bw.finish();
+			}
+			else if(type == SF_LPC && tid >= 64 && tid < 64 + order) {
+				const int i = tid - 64;
+				const uint32_t prec = (uint32_t)pl->precision;
+				bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)i * prec);
+				bw.put(mask_bits(pl->qlp[i], prec), prec);
+				bw.finish();
+			}
+			else if(predicted && tid == 96) {
+				bw.init(words, after_warm);
 				if(type == SF_LPC) {
 					bw.put((uint32_t)pl->precision - 1, kQlpPrecisionLen);
 					bw.put(mask_bits(pl->shift, kQlpShiftLen), kQlpShiftLen);
-					for(int i = 0; i < order; i++) bw.put(mask_bits(pl->qlp[i], (uint32_t)pl->precision), (uint32_t)pl->precision);
+					bw.finish();
+					bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)order * (uint32_t)pl->precision);
 				}
 				bw.put((uint32_t)pl->method, kEntropyTypeLen);
 				bw.put((uint32_t)pl->porder, kRiceOrderLen);
+				bw.finish();
 			}
-			bw.finish();
 		}
 		bitpos += hdr_bits;
 
@@ -676,19 +698,33 @@ __global__ void __launch_bounds__(NT) k_emit2(EncK P, const int32_t *__restrict_
 			const uint32_t byte = (words[b >> 2] >> (24 - 8 * ((uint32_t)b & 3))) & 0xffu;
 			crc = ((crc << 8) & 0xffffu) ^ s_crctab[((crc >> 8) ^ byte) & 0xffu];
 		}
-		s_crc[tid] = crc;
-		if(tid == 0) {
-			uint32_t result = 1, bb = 2, e = 8 * L;
-			while(e) {
-				if(e & 1) result = gf16_mul(result, bb);
-				bb = gf16_mul(bb, bb);
-				e >>= 1;
-			}
-			for(int s = 0; s < 8; s++) { s_mlev[s] = result; result = gf16_mul(result, result); }
+		// CRC of a concatenation: crc(A || B) = crc(A) * x^(8 len(B)) + crc(B) in GF(2)[x] / (x^16+x^15+x^2+1) (init 0).
+		// Level s of the combine tree needs x^(8 L 2^s); thread s builds it from the constants x^(2^j) (at most popcount(8L) products).
+		if(tid < 8) {
+			uint32_t e = (8u * L) << tid, m = 1;
+			for(int j = 0; e; j++, e >>= 1)
+				if(e & 1u) m = gf16_mul(m, kCrcXPow2[j % 15]);
+			s_mlev[tid] = m;
 		}
 		__syncthreads();
-		for(int s = 0; (1 << s) < NT; s++) {
-			if((tid & ((2 << s) - 1)) == 0) s_crc[tid] = gf16_mul(s_crc[tid], s_mlev[s]) ^ s_crc[tid + (1 << s)];
+		{
+			const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+			for(int sl = 0; sl < 5; sl++) {
+				const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << sl);
+				crc = gf16_mul(crc, s_mlev[sl]) ^ other;  // meaningful in lanes that are multiples of 2 << sl; lane 0 is what counts
+			}
+			if(lane == 0) s_crc[warp] = crc;
+			__syncthreads();
+			if(warp == 0) {
+				crc = lane < NW ? s_crc[lane] : 0;
+#pragma unroll
+				for(int sl = 0; (1 << sl) < NW; sl++) {
+					const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << sl);
+					crc = gf16_mul(crc, s_mlev[5 + sl]) ^ other;
+				}
+				if(lane == 0) s_crc[0] = crc;
+			}
 			__syncthreads();
 		}
 	}

@@ -32,6 +32,38 @@ __host__ __device__ constexpr size_t search4_bytes_per_warp(int bs, int R_T)
 	return ((size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared4) + 15) / 16 * 16;
 }
 
+// int32 -> double without the conversion pipe: the bit pattern 0x43300000:(x ^ 0x80000000) is 2^52 + 2^31 + x.
+__device__ __forceinline__ double int_to_double_exact(int x)
+{
+	return __dsub_rn(__hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)), 4503601774854144.0);
+}
+
+// The 64-bit-accumulator predictor (lpc.c:786-884, subframes deeper than 16 bits) on the FP64 pipe. Measured on
+// B200 (tools/ubench): IMAD.WIDE chains run at ~13 lanes/clk/SM, DFMA at ~57. Everything here is an integer
+// below 2^51 held in a double, so every operation is exact: qd[j] = q[j] * 2^-shift (a power-of-two scaling keeps
+// the significand), sum = sum_j qd[j] x[i-1-j] = (integer sum) / 2^shift, floor(sum) by adding 1.5 * 2^52 rounding
+// down (== the reference's arithmetic right shift), |residual| added into a double (< 2^45 per run).
+template <int G, int MAXORD, int NTAPS, bool MASKED>
+__device__ __forceinline__ void group_abs_sum_f64(const int (&xg)[MAXORD + G], const double (&qd)[MAXORD], int ord0, int limit, double &sd, bool &bad)
+{
+	constexpr double kFloorMagic = 6755399441055744.0;  // 1.5 * 2^52
+	double xd[MAXORD + G];
+#pragma unroll
+	for(int i = MAXORD - NTAPS; i < MAXORD + G; i++) xd[i] = int_to_double_exact(xg[i]);
+#pragma unroll
+	for(int m = 0; m < G; m++) {
+		double sum = 0.0;
+#pragma unroll
+		for(int j = 0; j < NTAPS; j++) sum = fma(qd[j], xd[MAXORD + m - 1 - j], sum);
+		const double t = __dadd_rd(sum, kFloorMagic);                          // floor(sum) + magic
+		const double rr = __dadd_rn(__dsub_rn(xd[MAXORD + m], t), kFloorMagic);  // x - floor(sum): the residual
+		if(limit && (rr <= -2147483648.0 || rr > 2147483647.0)) bad = true;    // lpc.c:868-884
+		bool keep = true;
+		if(MASKED && m < MAXORD) keep = m >= ord0;
+		if(keep) sd = __dadd_rn(sd, fabs(rr));
+	}
+}
+
 // All runs of one candidate: leaf[p] = sum of |residual| over finest partition p.
 // xs = first sample of the warp's slice (row stride 36 words, kSearch4ZeroRow zero words in front).
 // lpp_log: log2(lanes per partition) when a partition fits in a tile (tpp == 1), else tpp tiles make one partition.
@@ -43,11 +75,18 @@ __device__ __forceinline__ bool fir_partition_sums(const int32_t *xs, const int 
 	constexpr int G = (R_T == 32) ? 16 : 12, NG = R_T / G, ROWPAD = 36 - R_T;
 	bool bad = false;
 	unsigned long long carry = 0;
+	double qd[MAXORD];
+	if(WIDE) {
+		const double scale = __hiloint2double((1023 - shift) << 20, 0);  // 2^-shift
+#pragma unroll
+		for(int j = 0; j < MAXORD; j++) qd[j] = __dmul_rn((double)q[j], scale);
+	}
 #pragma unroll 1
 	for(int t = 0; t < ntiles; t++) {
 		const int32_t *rowp = xs + (t * 32 + lane) * 36;
 		uint32_t s32 = 0;
 		unsigned long long s64 = 0;
+		double sd = 0.0;
 #pragma unroll 1
 		for(int g = 0; g < NG; g++) {
 			int xg[MAXORD + G];
@@ -67,10 +106,13 @@ __device__ __forceinline__ bool fir_partition_sums(const int32_t *xs, const int 
 			if(t == 0) {
 				// warm-up samples of the block (the first `order` outputs of row 0) are not residuals
 				const int ord_g = lane == 0 ? order - g * G : 0;
-				group_abs_sum<G, MAXORD, NTAPS, WIDE, true, NARROW>(xg, q, shift, ord_g, limit, s32, s64, bad);
+				if(WIDE) group_abs_sum_f64<G, MAXORD, NTAPS, true>(xg, qd, ord_g, limit, sd, bad);
+				else group_abs_sum<G, MAXORD, NTAPS, false, true, NARROW>(xg, q, shift, ord_g, limit, s32, s64, bad);
 			}
-			else group_abs_sum<G, MAXORD, NTAPS, WIDE, false, NARROW>(xg, q, shift, 0, limit, s32, s64, bad);
+			else if(WIDE) group_abs_sum_f64<G, MAXORD, NTAPS, false>(xg, qd, 0, limit, sd, bad);
+			else group_abs_sum<G, MAXORD, NTAPS, false, false, NARROW>(xg, q, shift, 0, limit, s32, s64, bad);
 		}
+		if(WIDE) s64 = (unsigned long long)__double2ll_rn(sd);  // an exact non-negative integer
 		if(tpp == 1) {
 			const int lpp = 1 << lpp_log;
 			if(NARROW) {
