@@ -5,13 +5,14 @@
 Flags that matter for bit-exactness: -fmad=false (no FMA contraction of the LPC analysis),
 host side -ffp-contract=off (window tables use the host libm exactly like the reference).
 """
+import glob
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("encoder.cu", "decoder.cu", "stream_api.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("fb200_internal.h", "encode_kernels.cuh", "encode_kernels_v2.cuh", "encode_kernels_v3.cuh", "decode_kernels.cuh")] + [
+HDR = sorted(glob.glob(os.path.join(HERE, "csrc", "*.h")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [
     os.path.join(HERE, "..", "include", "flac_b200.h"), os.path.join(HERE, "..", "include", "flac_b200_stream.h")]
 OUT = os.path.join(HERE, "libflac_b200.so")
 

@@ -81,6 +81,36 @@ __device__ __forceinline__ bool fir_partition_sums(const int32_t *xs, const int 
 #pragma unroll
 		for(int j = 0; j < MAXORD; j++) qd[j] = __dmul_rn((double)q[j], scale);
 	}
+	// The pass below treats every sample as a residual (one code path, half the instruction footprint of a
+	// masked first tile). The first `order` outputs of the block are warm-up samples, not residuals: their
+	// |"residual"| (history before the block = the zero row) is recomputed here and taken out of partition 0.
+	unsigned long long warm = 0;
+	{
+		int xw[MAXORD];
+#pragma unroll
+		for(int k = 0; k < MAXORD / 4; k++) {
+			const int4 v = *reinterpret_cast<const int4 *>(xs + 4 * k);
+			xw[4 * k] = v.x; xw[4 * k + 1] = v.y; xw[4 * k + 2] = v.z; xw[4 * k + 3] = v.w;
+		}
+#pragma unroll
+		for(int m = 0; m < MAXORD; m++) {
+			unsigned long long a;
+			if(!WIDE) {
+				int sum = 0;
+#pragma unroll
+				for(int j = 0; j < (m < NTAPS ? m : NTAPS); j++) sum += q[j] * xw[m - 1 - j];
+				a = __sad(xw[m], sum >> shift, 0u);
+			}
+			else {
+				long long sum = 0;
+#pragma unroll
+				for(int j = 0; j < (m < NTAPS ? m : NTAPS); j++) sum += (long long)q[j] * (long long)xw[m - 1 - j];
+				const long long rr = (long long)xw[m] - (sum >> shift);
+				a = (unsigned long long)(rr < 0 ? -rr : rr);
+			}
+			if(m < order) warm += a;
+		}
+	}
 #pragma unroll 1
 	for(int t = 0; t < ntiles; t++) {
 		const int32_t *rowp = xs + (t * 32 + lane) * 36;
@@ -103,13 +133,7 @@ __device__ __forceinline__ bool fir_partition_sums(const int32_t *xs, const int 
 				const int4 v = *reinterpret_cast<const int4 *>(op + 4 * k);
 				xg[MAXORD + 4 * k] = v.x; xg[MAXORD + 4 * k + 1] = v.y; xg[MAXORD + 4 * k + 2] = v.z; xg[MAXORD + 4 * k + 3] = v.w;
 			}
-			if(t == 0) {
-				// warm-up samples of the block (the first `order` outputs of row 0) are not residuals
-				const int ord_g = lane == 0 ? order - g * G : 0;
-				if(WIDE) group_abs_sum_f64<G, MAXORD, NTAPS, true>(xg, qd, ord_g, limit, sd, bad);
-				else group_abs_sum<G, MAXORD, NTAPS, false, true, NARROW>(xg, q, shift, ord_g, limit, s32, s64, bad);
-			}
-			else if(WIDE) group_abs_sum_f64<G, MAXORD, NTAPS, false>(xg, qd, 0, limit, sd, bad);
+			if(WIDE) group_abs_sum_f64<G, MAXORD, NTAPS, false>(xg, qd, 0, limit, sd, bad);
 			else group_abs_sum<G, MAXORD, NTAPS, false, false, NARROW>(xg, q, shift, 0, limit, s32, s64, bad);
 		}
 		if(WIDE) s64 = (unsigned long long)__double2ll_rn(sd);  // an exact non-negative integer
@@ -118,16 +142,19 @@ __device__ __forceinline__ bool fir_partition_sums(const int32_t *xs, const int 
 			if(NARROW) {
 				uint32_t s = s32;  // the reference's 32-bit accumulator wraps (stream_encoder.c:4815-4824); so does this
 				for(int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+				if(t == 0 && lane == 0) s -= (uint32_t)warm;
 				if((lane & (lpp - 1)) == 0) leaf[(t * 32 + lane) >> lpp_log] = s;
 			}
 			else {
 				unsigned long long s = s64;
 				for(int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+				if(t == 0 && lane == 0) s -= warm;
 				if((lane & (lpp - 1)) == 0) leaf[(t * 32 + lane) >> lpp_log] = mask32 ? (unsigned long long)(uint32_t)s : s;
 			}
 		}
 		else {
 			carry += warp_sum_u64(NARROW ? (unsigned long long)s32 : s64);
+			if(t + 1 == tpp) carry -= warm;
 			if((t + 1) % tpp == 0) {
 				if(lane == 0) leaf[t / tpp] = (NARROW || mask32) ? (unsigned long long)(uint32_t)carry : carry;
 				carry = 0;
@@ -289,7 +316,7 @@ __global__ void __launch_bounds__(NW * 32) k_search4(EncK P, const int32_t *__re
 			const int myL = (int)ilog2_u32((uint32_t)n1);
 			const int myP = n1 - (1 << myL);
 			unsigned long long mine = 0;
-#pragma unroll
+#pragma unroll 1
 			for(int L = 4; L >= 0; L--) {
 				if(L < lev) cur += __shfl_xor_sync(0xffffffffu, cur, 16 >> L);  // two order-(L+1) groups make one order-L group
 				const unsigned long long got = __shfl_sync(0xffffffffu, cur, (myP << (5 - L)) & 31);
@@ -299,9 +326,9 @@ __global__ void __launch_bounds__(NW * 32) k_search4(EncK P, const int32_t *__re
 			const bool active = lane < 31 && myL >= min_po && myL <= top;
 			const uint32_t psamp = (uint32_t)(bs >> myL) - (myP == 0 ? (uint32_t)order : 0u);
 			const uint32_t bits = node_bits(mine, psamp, 0x40000u / psamp, n1, active);
-#pragma unroll
-			for(int L = 4; L >= 0; L--)
-				if(L <= top && L >= min_po) close_order(L, (active && myL == L) ? bits : 0u);
+#pragma unroll 1
+			for(int L = top; L >= min_po; L--)
+				if(true) close_order(L, (active && myL == L) ? bits : 0u);
 		}
 
 		uint32_t estimate = kSubframeHeaderBits + (uint32_t)wasted;
