@@ -426,12 +426,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 	__syncthreads();
 	const uint32_t res = s_warp[warp] + inc - v;
 	*total = s_warp[NW];
-	__syncthreads();
-	return res;
+	return res;  // callers place a barrier before the next scan reuses s_warp (k_emit2: the end-of-channel barrier)
 }
 
 template <int NT, int R_T, int MAXORD, bool R_EXACT>
-__global__ void __launch_bounds__(NT) k_emit2(EncK P, const int32_t *__restrict__ sig, const int *__restrict__ blkflags,
+// 256-thread CTAs: three per SM (shared memory allows it), which caps the kernel at 80 registers per thread
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) k_emit2(EncK P, const int32_t *__restrict__ sig, const int *__restrict__ blkflags,
                                              const SubframePlan *__restrict__ plans, uint8_t *__restrict__ slots,
                                              uint32_t *__restrict__ frame_bytes, uint32_t *__restrict__ chan_assign_out)
 {
@@ -646,41 +646,72 @@ __global__ void __launch_bounds__(NT) k_emit2(EncK P, const int32_t *__restrict_
 			const int psize = bs >> po;
 			const uint32_t plen = pl->method ? kRice2ParamLen : kRiceParamLen;
 			uint32_t mybits = 0;
-			{
-				int p = base / psize;
-				int next = (p + 1) * psize;
-				uint32_t k = __ldg(&pl->params[p]);
+			// A run of R_T samples lies inside one partition whenever the partition size is a multiple of R_T (always for
+			// the standard blocksizes and orders <= 8 here): one Rice parameter per run, and the parameter field precedes
+			// exactly one position -- `order` in partition 0, the partition's first sample elsewhere.
+			const bool one_partition = R_EXACT && (psize % R_T) == 0;
+			uint32_t total;
+			if(one_partition) {
+				const int p = base / psize;
+				const uint32_t k = __ldg(&pl->params[p]);
+				const int first_res = p == 0 ? order : p * psize;
+				uint32_t u[R_T];
 #pragma unroll
 				for(int m = 0; m < R_T; m++) {
-					const int i = base + m;
-					if((R_EXACT || m < R) && i >= order) {
-						if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
-						if(i == p * psize || i == order) mybits += plen;
-						const uint32_t u = ((uint32_t)r[m] << 1) ^ (uint32_t)(r[m] >> 31);
-						mybits += (u >> k) + 1 + k;
+					u[m] = ((uint32_t)r[m] << 1) ^ (uint32_t)(r[m] >> 31);
+					if(base + m >= order) mybits += (u[m] >> k) + 1 + k + (base + m == first_res ? plen : 0u);
+				}
+				const uint32_t start = block_exclusive_scan<NT>(mybits, s_warp, &total);
+				if(mybits) {
+					BitPut bw;
+					bw.init(words, bitpos + start);
+#pragma unroll
+					for(int m = 0; m < R_T; m++) {
+						if(base + m >= order) {
+							if(base + m == first_res) bw.put(k, plen);
+							bw.skip(u[m] >> k);
+							bw.put((1u << k) | (u[m] & ((1u << k) - 1u)), k + 1);
+						}
 					}
+					bw.finish();
 				}
 			}
-			uint32_t total;
-			const uint32_t start = block_exclusive_scan<NT>(mybits, s_warp, &total);
-			if(mybits) {
-				BitPut bw;
-				bw.init(words, bitpos + start);
-				int p = base / psize;
-				int next = (p + 1) * psize;
-				uint32_t k = __ldg(&pl->params[p]);
+			else {
+				{
+					int p = base / psize;
+					int next = (p + 1) * psize;
+					uint32_t k = __ldg(&pl->params[p]);
 #pragma unroll
-				for(int m = 0; m < R_T; m++) {
-					const int i = base + m;
-					if((R_EXACT || m < R) && i >= order) {
-						if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
-						if(i == p * psize || i == order) bw.put(k, plen);
-						const uint32_t u = ((uint32_t)r[m] << 1) ^ (uint32_t)(r[m] >> 31);
-						bw.skip(u >> k);
-						bw.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
+					for(int m = 0; m < R_T; m++) {
+						const int i = base + m;
+						if((R_EXACT || m < R) && i >= order) {
+							if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
+							if(i == p * psize || i == order) mybits += plen;
+							const uint32_t u = ((uint32_t)r[m] << 1) ^ (uint32_t)(r[m] >> 31);
+							mybits += (u >> k) + 1 + k;
+						}
 					}
 				}
-				bw.finish();
+				const uint32_t start = block_exclusive_scan<NT>(mybits, s_warp, &total);
+				if(mybits) {
+					BitPut bw;
+					bw.init(words, bitpos + start);
+					int p = base / psize;
+					int next = (p + 1) * psize;
+					uint32_t k = __ldg(&pl->params[p]);
+#pragma unroll
+					for(int m = 0; m < R_T; m++) {
+						const int i = base + m;
+						if((R_EXACT || m < R) && i >= order) {
+							if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
+							if(i == p * psize || i == order) bw.put(k, plen);
+							const uint32_t u = ((uint32_t)r[m] << 1) ^ (uint32_t)(r[m] >> 31);
+							bw.skip(u >> k);
+							bw.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
+						}
+					}
+					bw.finish();
+				}
 			}
 			bitpos += total;
 		}
