@@ -317,8 +317,8 @@ static void set_smem_attrs(int search_bytes, int emit_bytes)
 	cudaFuncSetAttribute(k_search3<36, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 	cudaFuncSetAttribute(k_search3<32, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 	cudaFuncSetAttribute(k_search3<36, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	if(MO <= 12) {
-		constexpr int MO4 = MO <= 12 ? MO : 12;
+	{
+		constexpr int MO4 = MO;
 		cudaFuncSetAttribute(k_search4<32, MO4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 		cudaFuncSetAttribute(k_search4<36, MO4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 		cudaFuncSetAttribute(k_search4<32, MO4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
@@ -403,6 +403,7 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, int nb, uint32_t first_fra
 		// orders > 16 (found by tests/test_gpu_encode.py::test_option_matrix; not yet root-caused)
 		if(g.maxord_t == 8) launch_search4<8>(k, e, g, nitems, st);
 		else if(g.maxord_t == 12) launch_search4<12>(k, e, g, nitems, st);
+		else if(e->search_version >= 5) launch_search4<32>(k, e, g, nitems, st);  // FB200_SEARCH_KERNEL=5: experimental, see above
 		else launch_search3<32>(k, e, g, nitems, st);
 	}
 	else if(g.fast_search3 && !e->use_v1 && e->search_version >= 3) {
@@ -714,7 +715,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 		if(e->autoc_split) e->autoc_version = 2;
 		cudaFuncSetAttribute(k_autoc3<33, 132, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoc3_smem_bytes<33, 132, 1, 3>());
 		const char *sv = getenv("FB200_SEARCH_KERNEL");
-		if(sv && sv[0] >= '1' && sv[0] <= '4') e->search_version = sv[0] - '0';
+		if(sv && sv[0] >= '1' && sv[0] <= '5') e->search_version = sv[0] - '0';
 	}
 	*out = e;
 	return FB200_OK;

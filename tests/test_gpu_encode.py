@@ -171,3 +171,14 @@ def test_every_kernel_generation_is_bit_exact(env, level, ch, bps, monkeypatch):
     x = signals.music_like(4096 * 3 + 55, ch, bps, 44100, seed=17)
     got = _gpu_frames(x, bps, 44100, level)
     _assert_same(got, _oracle_frames(x, bps, 44100, level), f"{env}")
+
+
+@pytest.mark.xfail(strict=False, reason="k_search4's 32-tap instantiation mis-evaluated orders > 16 when first written; "
+                                        "the default path keeps k_search3 for max_lpc_order > 12 until this passes reliably")
+def test_search4_32tap_experimental(monkeypatch):
+    """FB200_SEARCH_KERNEL=5 forces k_search4 for max_lpc_order > 12 as well (not the default dispatch)."""
+    monkeypatch.setenv("FB200_SEARCH_KERNEL", "5")
+    for bps, mlo in ((16, 32), (12, 20), (24, 32)):
+        x = signals.music_like(4096 * 2 + 99, 2, bps, 44100, seed=2)
+        got = _gpu_frames(x, bps, 44100, 8, max_lpc_order=mlo)
+        _assert_same(got, _oracle_frames(x, bps, 44100, 8, max_lpc_order=mlo), f"bps {bps} max_lpc_order {mlo}")
