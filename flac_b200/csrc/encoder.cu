@@ -88,6 +88,7 @@ struct fb200_encoder {
 	size_t h_totals_cap = 0;
 	uint64_t launches = 0;
 	bool autoc_split = false;
+	int host_chunks = 12;   // chunks per fb200_encode_host call (FB200_HOST_CHUNKS): copy/compute overlap granularity; measured best 8-12 (tools/sweep_host_chunks.py)
 	int pipe_chunks = 1;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS); see fb200_encode_device
 	int autoc_version = 3;  // FB200_AUTOC_KERNEL=2 selects the thread-private-load generation (k_autoc2)
 	int search_version = 4;  // FB200_SEARCH_KERNEL=1|2|3|4 selects the search kernel generation (benchmarks/tests)
@@ -710,6 +711,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 		e->autoc_split = as && as[0] == '1';
 		const char *pc = getenv("FB200_PIPE_CHUNKS");
 		if(pc && atoi(pc) >= 1 && atoi(pc) <= 64) e->pipe_chunks = atoi(pc);
+		const char *hc = getenv("FB200_HOST_CHUNKS");
+		if(hc && atoi(hc) >= 1 && atoi(hc) <= 256) e->host_chunks = atoi(hc);
 		const char *av = getenv("FB200_AUTOC_KERNEL");
 		if(av && (av[0] == '2' || av[0] == '3')) e->autoc_version = av[0] - '0';
 		if(e->autoc_split) e->autoc_version = 2;
@@ -836,8 +839,8 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 	}
 	if(!e->s_h2d) FB_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
 	if(!e->s_d2h) FB_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
-	// chunking: ~5 chunks per call, between 256 blocks and the launch capacity; the short last block is its own chunk
-	uint64_t chunk = (nfull + 4) / 5;
+	// chunking: host_chunks (default 12) chunks per call, between 256 blocks and the launch capacity; the short last block is its own chunk
+	uint64_t chunk = (nfull + e->host_chunks - 1) / e->host_chunks;
 	if(chunk < 256) chunk = 256;
 	if(chunk > e->max_blocks) chunk = e->max_blocks;
 	std::vector<PipeChunk> chunks;
