@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -97,3 +98,46 @@ def test_setters_and_validation_without_device(lib):
     assert L.FLAC__stream_encoder_init_ogg_stream(e, None, None, None, None, None, None) == 2      # UNSUPPORTED_CONTAINER
     L.FLAC__stream_encoder_delete.argtypes = [C.c_void_p]
     L.FLAC__stream_encoder_delete(e)
+
+
+def test_crc16_power_table_constants():
+    """kCrcXPow2 in encode_kernels.cuh (x^(2^j) mod x^16+x^15+x^2+1, used to combine chunk CRCs) recomputed from
+    scratch, and the combine identity crc(A||B) = crc(A) * x^(8|B|) + crc(B) checked against a bytewise CRC-16."""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "flac_b200", "csrc", "encode_kernels.cuh")).read()
+    m = re.search(r"kCrcXPow2\[15\]\s*=\s*\{([^}]*)\}", src)
+    table = [int(v, 16) for v in m.group(1).replace(" ", "").split(",")]
+
+    def mul(a, b):
+        r = 0
+        for i in range(15, -1, -1):
+            r = ((r << 1) ^ 0x8005) & 0xFFFF if r & 0x8000 else (r << 1)
+            if (b >> i) & 1:
+                r ^= a
+        return r
+
+    v, want = 2, []
+    for _ in range(15):
+        want.append(v)
+        v = mul(v, v)
+    assert table == want and v == 2  # x has order 2^15 - 1: the table is periodic
+
+    def crc16(data, crc=0):
+        for byte in data:
+            crc ^= byte << 8
+            for _ in range(8):
+                crc = ((crc << 1) ^ 0x8005) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+        return crc
+
+    def xpow(e):
+        r, j = 1, 0
+        while e:
+            if e & 1:
+                r = mul(r, table[j % 15])
+            e >>= 1
+            j += 1
+        return r
+
+    rng = np.random.default_rng(3)
+    a, b = bytes(rng.integers(0, 256, 517, dtype=np.uint8)), bytes(rng.integers(0, 256, 4099, dtype=np.uint8))
+    assert crc16(a + b) == mul(crc16(a), xpow(8 * len(b))) ^ crc16(b)
