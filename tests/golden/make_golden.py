@@ -34,19 +34,28 @@ CASES = [
     ("noisy_sine_l8", "noisy_sine", dict(nsamples=4096 * 2, channels=2, bps=16), 16, 44100, 8, 0),
     ("bs1000_l5", "music_like", dict(nsamples=3300, channels=2, bps=16, rate=44100, seed=3), 16, 44100, 5, 1000),
     ("bs4608_l8", "music_like", dict(nsamples=4608 * 2 + 10, channels=2, bps=16, rate=44100, seed=3), 16, 44100, 8, 4608),
+    # apodization specification strings (8th field), FLAC__stream_encoder_set_apodization
+    ("music16_l8_pre14_windows", "music_like", dict(nsamples=4096 * 2 + 100, channels=2, bps=16, rate=44100, seed=21), 16, 44100, 8, 0,
+     "tukey(0.25);partial_tukey(2);punchout_tukey(3)"),
+    ("music16_l5_gauss", "music_like", dict(nsamples=4096 * 2 + 100, channels=2, bps=16, rate=44100, seed=22), 16, 44100, 5, 0, "gauss(0.2)"),
+    ("music24_l8_welch_hann", "music_like", dict(nsamples=4096 * 2 + 9, channels=2, bps=24, rate=96000, seed=23), 24, 96000, 8, 0, "welch;hann"),
+    ("music16_l5_bs1152_triangle_connes", "music_like", dict(nsamples=1152 * 3 + 5, channels=2, bps=16, rate=44100, seed=24), 16, 44100, 5, 1152,
+     "triangle;connes;rectangle"),
 ]
 
 
 def main():
     out = {"reference": reflib.lib().ref_version().decode(), "build": "oracle/Makefile ref (gcc -O3, shipped FP flags)", "cases": {}}
-    for name, gen, kw, bps, rate, level, bs in CASES:
+    for name, gen, kw, bps, rate, level, bs, *rest in CASES:
+        apod = rest[0] if rest else None
         x = getattr(signals, gen)(**kw)
-        opts = reflib.RefEncOpts(streamable_subset=0)
+        opts = reflib.RefEncOpts(streamable_subset=0, **({"apodization": apod} if apod else {}))
         _, _, fd = reflib.encode(x, bps, rate=rate, level=level, blocksize=bs, variant="default", opts=opts)
         _, _, fs = reflib.encode(x, bps, rate=rate, level=level, blocksize=bs, variant="strict", opts=opts)
         assert fd == fs, f"{name}: reference builds disagree"
         out["cases"][name] = {
             "generator": gen, "kwargs": kw, "bps": bps, "rate": rate, "level": level, "blocksize": bs,
+            **({"apodization": apod} if apod else {}),
             "input_sha256": hashlib.sha256(x.tobytes()).hexdigest(),
             "frame_sizes": [len(f) for f in fd],
             "frame_sha256": [hashlib.sha256(f).hexdigest() for f in fd],

@@ -20,6 +20,10 @@ def _input(case):
     return x
 
 
+def _over(case):
+    return {"apodization": case["apodization"]} if "apodization" in case else {}
+
+
 def _check(frames, case):
     assert [len(f) for f in frames] == case["frame_sizes"]
     assert [hashlib.sha256(f).hexdigest() for f in frames] == case["frame_sha256"]
@@ -30,7 +34,7 @@ def _check(frames, case):
 def test_oracle_reproduces_golden_frames(name):
     case = GOLD["cases"][name]
     x = _input(case)
-    enc = oraclelib.Encoder(oraclelib.preset(x.shape[1], case["bps"], case["rate"], case["level"], case["blocksize"]))
+    enc = oraclelib.Encoder(oraclelib.preset(x.shape[1], case["bps"], case["rate"], case["level"], case["blocksize"], **_over(case)))
     _check(enc.encode_stream(x), case)
 
 
@@ -40,7 +44,7 @@ def test_cuda_reproduces_golden_frames(name):
     import flac_b200
     case = GOLD["cases"][name]
     x = _input(case)
-    enc = flac_b200.Encoder(flac_b200.preset(x.shape[1], case["bps"], case["rate"], case["level"], case["blocksize"]))
+    enc = flac_b200.Encoder(flac_b200.preset(x.shape[1], case["bps"], case["rate"], case["level"], case["blocksize"], **_over(case)))
     _check(enc.encode_frames(x), case)
     enc.close()
 
@@ -52,7 +56,7 @@ def test_cuda_decodes_golden_inputs(name):
     import flac_b200
     case = GOLD["cases"][name]
     x = _input(case)
-    enc = flac_b200.Encoder(flac_b200.preset(x.shape[1], case["bps"], case["rate"], case["level"], case["blocksize"]))
+    enc = flac_b200.Encoder(flac_b200.preset(x.shape[1], case["bps"], case["rate"], case["level"], case["blocksize"], **_over(case)))
     stream, offs = enc.encode(x)
     dec = flac_b200.Decoder(x.shape[1], case["bps"], case["rate"], enc.cfg.blocksize)
     y = dec.decode(stream, offs, total_samples=x.shape[0])
