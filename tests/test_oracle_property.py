@@ -1,0 +1,62 @@
+"""Property check (CPU): for randomly drawn configurations the oracle's frames equal the compiled reference's
+(source-order FP build), frame for frame. Deterministic (derandomized hypothesis), bounded to a few seconds."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import oraclelib
+import reflib
+import signals
+from conftest import require_ref
+
+APODS = [None, "tukey(0.5)", "subdivide_tukey(3)", "hann", "welch;gauss(0.3)", "partial_tukey(2/0.2);punchout_tukey(2)", "rectangle;triangle", "tukey(0.1);connes"]
+SIGNALS = ["music_like", "white_noise", "noisy_sine", "wasted_bits"]
+
+
+def _signal(kind, n, ch, bps, seed):
+    if kind == "music_like":
+        return signals.music_like(n, ch, bps, 44100, seed=seed)
+    if kind == "white_noise":
+        return signals.white_noise(n, ch, bps, seed=seed, scale=0.05)
+    if kind == "noisy_sine":
+        return signals.noisy_sine(n, ch, bps)
+    return signals.wasted_bits(n, ch, bps, 2)
+
+
+@settings(max_examples=400, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(ch=st.integers(1, 2), bps=st.sampled_from([8, 12, 16, 20, 24]), level=st.integers(0, 8),
+       bs=st.sampled_from([0, 192, 576, 1000, 1152, 2048, 4096, 4608]), kind=st.sampled_from(SIGNALS), seed=st.integers(1, 50),
+       apod=st.sampled_from(APODS), exhaustive=st.booleans(), max_order=st.sampled_from([None, 4, 10, 16, 32]),
+       precision=st.sampled_from([None, 7, 11, 14]), po=st.sampled_from([None, (0, 3), (2, 2), (0, 8)]), loose=st.booleans())
+def test_oracle_equals_reference_on_random_configurations(ch, bps, level, bs, kind, seed, apod, exhaustive, max_order, precision, po, loose):
+    require_ref("strict")
+    bsz = bs or (1152 if level < 3 else 4096)
+    n = bsz * 2 + 37
+    x = _signal(kind, n, ch, bps, seed)
+    okw, rkw = {}, {}
+    if apod:
+        okw["apodization"] = rkw["apodization"] = apod
+    if exhaustive and (max_order or 8) <= 10:  # keep the exhaustive search small
+        okw["do_exhaustive_model_search"] = 1; rkw["exhaustive"] = 1
+    if max_order is not None:
+        okw["max_lpc_order"] = max_order; rkw["max_lpc_order"] = max_order
+    if precision is not None:
+        okw["qlp_coeff_precision"] = precision; rkw["qlp_precision"] = precision
+    if po is not None:
+        okw["min_residual_partition_order"], okw["max_residual_partition_order"] = po
+        rkw["min_part_order"], rkw["max_part_order"] = po
+    if loose and ch == 2:
+        okw["do_mid_side"] = 1; okw["loose_mid_side"] = 1
+        rkw["mid_side"] = 1; rkw["loose_mid_side"] = 1
+    try:
+        enc = oraclelib.Encoder(oraclelib.preset(ch, bps, 44100, level, bs, **okw))
+    except ValueError:
+        return  # outside the oracle's declared scope
+    got = enc.encode_stream(x)
+    try:
+        _, _, ref = reflib.encode(x, bps, rate=44100, level=level, blocksize=bs, variant="strict", opts=reflib.RefEncOpts(streamable_subset=0, **rkw))
+    except RuntimeError:
+        return  # the reference rejects this combination at init (e.g. precision too high for the sample width)
+    assert len(got) == len(ref)
+    bad = [i for i, (a, b) in enumerate(zip(got, ref)) if a != b]
+    assert not bad, f"frames {bad} differ"
