@@ -90,6 +90,11 @@ def lib():
     L.fb200_encoder_launch_count.argtypes = [C.c_void_p]
     L.fb200_encode_host.restype = C.c_int
     L.fb200_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32)]
+    L.fb200_encode_host_packed.restype = C.c_int
+    L.fb200_encode_host_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                           C.POINTER(C.c_uint32)]
+    L.fb200_encoder_set_file_blocks.restype = C.c_int
+    L.fb200_encoder_set_file_blocks.argtypes = [C.c_void_p, C.c_uint32]
     L.fb200_encode_device.restype = C.c_int
     L.fb200_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p, C.c_int]
@@ -122,6 +127,16 @@ def lib():
 def _check(rc):
     if rc != FB200_OK:
         raise FlacB200Error(rc, lib().fb200_last_error().decode(errors="replace"))
+
+
+def pack_pcm(pcm, bytes_per_sample):
+    """int32 [samples, channels] -> packed little-endian bytes (what a WAV data chunk holds)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    if bytes_per_sample == 2:
+        return pcm.astype("<i2").view(np.uint8).reshape(-1)
+    if bytes_per_sample == 3:
+        return np.ascontiguousarray(pcm.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1)
+    return pcm.astype("<i4").view(np.uint8).reshape(-1)
 
 
 def preset(channels, bits_per_sample, sample_rate, compression_level, blocksize=0, **overrides):
@@ -188,6 +203,24 @@ class Encoder:
                                        offsets.ctypes.data, C.byref(nf)))
         assert nf.value == nfr
         return out[:int(offsets[nfr])], offsets
+
+    def encode_packed(self, packed, bytes_per_sample, samples, first_frame_number=0, out=None, offsets=None):
+        """packed: uint8 ndarray of little-endian signed samples (2 or 3 bytes each, interleaved), `samples` per channel."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        assert packed.size == samples * self.cfg.channels * bytes_per_sample
+        nfr = self.num_frames(samples)
+        if out is None:
+            out = np.empty(nfr * self.max_frame_bytes + 64, dtype=np.uint8)
+        if offsets is None:
+            offsets = np.zeros(nfr + 1, dtype=np.uint64)
+        nf = C.c_uint32(0)
+        _check(lib().fb200_encode_host_packed(self._h, packed.ctypes.data, bytes_per_sample, samples, first_frame_number, out.ctypes.data,
+                                              out.size, offsets.ctypes.data, C.byref(nf)))
+        assert nf.value == nfr
+        return out[:int(offsets[nfr])], offsets
+
+    def set_file_blocks(self, blocks_per_file):
+        _check(lib().fb200_encoder_set_file_blocks(self._h, blocks_per_file))
 
     def encode_frames(self, pcm, first_frame_number=0):
         stream, offs = self.encode(pcm, first_frame_number)

@@ -25,7 +25,7 @@
 // double, so their product is exact in double and only the addition rounds.
 #pragma once
 
-#include "encode_kernels.cuh"
+#include "device_common.cuh"
 
 namespace fb200 {
 

@@ -1,0 +1,684 @@
+// emit_kernel.cuh -- k_emit3: one CTA per frame, frame assembled in shared memory and stored straight to its
+// final place in the output stream.
+//
+// Replaces k_emit2 + k_scan + k_gather and the per-frame slot buffer for 1- and 2-channel streams.
+// Reference semantics kept bit for bit: FLAC__frame_add_header (stream_encoder_framing.c:245-391),
+// FLAC__subframe_add_* (:393-520), add_residual_partitioned_rice_ (:538-594),
+// FLAC__bitwriter_write_rice_signed_block (bitwriter.c:575-706), zero pad + CRC-16 (stream_encoder.c:3465-3480,
+// crc.c:376-396), channel assignment argmin (stream_encoder.c:3937-3972).
+//
+// What round 1's k_emit2 spent its time on (ncu, profiles/r1g_full_cfg2.csv): ~158 thread-instructions per
+// sample, 31 % of the stall samples at block barriers (14+ barriers per frame: one exclusive scan and one
+// re-staging per channel), 11.6 M shared-memory bank conflicts, a byte-at-a-time CRC, a worst-case zero fill and
+// a slot -> gather double copy.  This kernel:
+//   * stages the caller's interleaved int32 block ONCE with a 1-D TMA bulk copy (cp.async.bulk + mbarrier), forms
+//     the two signals the channel assignment picked (L/R/M/S, wasted bits shifted out) in place;
+//   * a thread owns one run of R_T consecutive samples of one channel (row layout of k_search4: 36-word rows ->
+//     every 128-bit access is conflict free); residual, zig-zag and bit count in one rolled pass that writes the
+//     zig-zagged residuals back in place; ONE block scan for the whole frame (both channels);
+//   * runs are packed independently MSB-first (unary zeros + stop bit + k low bits go out as one field whenever they
+//     fit 32 bits); only the first/last word of a run is shared with a neighbour (atomicOr);
+//   * the frame is laid into shared memory so that its END is word aligned: the CRC-16 is a slicing-by-4 pass over
+//     equal word chunks + GF(2) combine, with no alignment cases;
+//   * frame offsets come from a single-pass decoupled look-back over frame byte counts; the frame is written
+//     directly to out + offset.
+#pragma once
+
+#include "device_common.cuh"
+#include "search_kernel.cuh"  // row layout constants (kSearch4ZeroRow)
+
+namespace fb200 {
+
+// ---------------------------------------------------------------- CRC-16 slicing tables
+// T[k][b] = CRC-16 (poly 0x8005, init 0, MSB first; crc.c:78-342) of byte b followed by k zero bytes.
+// Filled once per device by k_crc16_tables (encoder.cu uploads nothing: the table is computed on the device).
+__global__ void k_crc16_tables(uint16_t *__restrict__ tab)
+{
+	const int b = threadIdx.x;
+	uint32_t c = (uint32_t)b << 8;
+#pragma unroll
+	for(int j = 0; j < 8; j++) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) & 0xffffu : (c << 1) & 0xffffu;
+	tab[b] = (uint16_t)c;
+	__syncthreads();
+	uint32_t prev = c;
+	for(int k = 1; k < 4; k++) {
+		prev = ((prev << 8) & 0xffffu) ^ tab[prev >> 8];
+		tab[k * 256 + b] = (uint16_t)prev;
+	}
+}
+
+// decoupled look-back status word: value << 24 | epoch (22 bits) << 2 | flag (1 aggregate, 2 inclusive prefix)
+__device__ __forceinline__ unsigned long long lb_pack(unsigned long long value, unsigned epoch, unsigned flag)
+{
+	return (value << 24) | ((unsigned long long)(epoch & kLbEpochMask) << 2) | flag;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.volatile.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+struct RunPacker {
+	uint32_t *words;
+	uint32_t cur, pos;
+	int widx;
+	bool shared_first;
+	__device__ __forceinline__ void init(uint32_t *w, uint32_t bitpos)
+	{
+		words = w; pos = bitpos; widx = (int)(bitpos >> 5); cur = 0; shared_first = true;
+	}
+	__device__ __forceinline__ void store()
+	{
+		if(shared_first) { if(cur) atomicOr(&words[widx], cur); }
+		else words[widx] = cur;  // interior word: exclusively this run's, buffer pre-zeroed
+		shared_first = false;
+	}
+	// n zero bits
+	__device__ __forceinline__ void skip(uint32_t n)
+	{
+		pos += n;
+		const int nw = (int)(pos >> 5);
+		if(nw != widx) { if(cur || !shared_first) store(); shared_first = false; widx = nw; cur = 0; }
+	}
+	// 1..32 bits, value < 2^nbits
+	__device__ __forceinline__ void put(uint32_t value, uint32_t nbits)
+	{
+		const uint32_t off = pos & 31u;
+		const unsigned long long v = (unsigned long long)value << (64u - off - nbits);
+		cur |= (uint32_t)(v >> 32);
+		pos += nbits;
+		if(off + nbits >= 32u) {
+			store();
+			widx++;
+			cur = (uint32_t)v;
+		}
+	}
+	__device__ __forceinline__ void finish()
+	{
+		if(cur) atomicOr(&words[widx], cur);  // last (partial) word may be shared with the next run
+	}
+};
+
+// residuals of G consecutive outputs (narrow: 32-bit accumulation, lpc.c:321-553; wide: the 64-bit predictor on
+// the FP64 pipe, exact -- see group_abs_sum_f64)
+template <int G, int MAXORD, int NTAPS>
+__device__ __forceinline__ void group_residual_narrow(const int (&xg)[MAXORD + G], const int (&q)[MAXORD], int shift, int (&r)[G])
+{
+#pragma unroll
+	for(int m = 0; m < G; m++) {
+		int sum = 0;
+#pragma unroll
+		for(int j = 0; j < NTAPS; j++) sum += q[j] * xg[MAXORD + m - 1 - j];
+		r[m] = xg[MAXORD + m] - (sum >> shift);
+	}
+}
+
+template <int G, int MAXORD, int NTAPS>
+__device__ __forceinline__ void group_residual_wide(const int (&xg)[MAXORD + G], const int (&q)[MAXORD], int shift, int (&r)[G])
+{
+	constexpr double kFloorMagic = 6755399441055744.0;  // 1.5 * 2^52
+	const double scale = __hiloint2double((1023 - shift) << 20, 0);  // 2^-shift: qd = q / 2^shift keeps the significand
+	double qd[NTAPS];
+#pragma unroll
+	for(int j = 0; j < NTAPS; j++) qd[j] = __dmul_rn((double)q[j], scale);
+	double xd[MAXORD + G];
+#pragma unroll
+	for(int i = MAXORD - NTAPS; i < MAXORD + G; i++) xd[i] = int_to_double_exact(xg[i]);
+#pragma unroll
+	for(int m = 0; m < G; m++) {
+		double sum = 0.0;
+#pragma unroll
+		for(int j = 0; j < NTAPS; j++) sum = fma(qd[j], xd[MAXORD + m - 1 - j], sum);
+		const double t = __dadd_rd(sum, kFloorMagic);                            // floor(sum) + magic
+		const double rr = __dadd_rn(__dsub_rn(xd[MAXORD + m], t), kFloorMagic);  // x - floor(sum), an exact integer
+		r[m] = __double2loint(__dadd_rn(rr, kFloorMagic));                        // low word of (magic + rr) == (int)rr
+	}
+}
+
+// R_T: samples per run (32 or 36); MAXORD: 8 / 12 / 32; CH: channels in the stream (1 or 2).
+// blockDim.x = NT = (bs / R_T) * CH <= 256 (a power of two, TPC = bs / R_T >= 32).
+template <int R_T, int MAXORD, int CH>
+__global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
+{
+	static_assert(R_T == 32 || R_T == 36, "run length");
+	static_assert(CH == 1 || CH == 2, "resident emit path: 1 or 2 channels");
+	constexpr int G = (R_T == 32) ? 16 : 12, NG = R_T / G, ROWPAD = 36 - R_T;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int tid = threadIdx.x, NT = blockDim.x, bs = P.bs, lane = tid & 31, warp = tid >> 5;
+	const int TPC = bs / R_T;  // threads (runs) per channel
+	const int planar_words = kSearch4ZeroRow + TPC * 36;
+	Emit3Shared &S = *reinterpret_cast<Emit3Shared *>(smem_raw);
+	int32_t *const planar = reinterpret_cast<int32_t *>(smem_raw + (sizeof(Emit3Shared) + 15) / 16 * 16);
+	uint32_t *const words = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(planar) + emit3_sig_bytes(bs, R_T, CH));
+	const int words_cap = P.slot_words + 8;
+	uint16_t *const crc_tab = reinterpret_cast<uint16_t *>(planar);  // loaded after the pack pass, when the signals are dead
+	uint64_t *const mbar = reinterpret_cast<uint64_t *>(&S.mbar);
+
+	// ---- which frame: tickets are handed out in launch order, so every lower-numbered frame's CTA is already running
+	if(tid == 0) S.blk = (int)(atomicAdd(A.ticket, 1u) - A.ticket_base);
+	__syncthreads();
+	const int blk = S.blk;
+	const SubframePlan *bp = A.plans + (size_t)blk * P.nsig;
+
+	// ---- raw block -> shared memory with one TMA bulk copy; issued first so that it overlaps the prologue
+	const unsigned raw_bytes = (unsigned)bs * CH * 4u;
+	int32_t *const raw = planar;  // lands where the planar signals will be: it is pulled into registers first
+	if(tid == 0) {
+		mbar_init(mbar, 1);
+		mbar_fence_init();
+		mbar_expect_tx(mbar, raw_bytes);
+		tma_bulk_g2s(raw, A.pcm + (size_t)blk * bs * CH, raw_bytes, mbar);
+	}
+
+	// ---- channel assignment (stream_encoder.c:3937-3972) and what it implies
+	int ca = 0;
+	if(CH == 2 && P.do_ms) {
+		if(P.loose_ms) ca = (__ldg(&A.blkflags[blk]) & 2) ? 3 : 0;
+		else {
+			const uint32_t e0 = __ldg(&bp[0].est_bits), e1 = __ldg(&bp[1].est_bits), e2 = __ldg(&bp[2].est_bits), e3 = __ldg(&bp[3].est_bits);
+			const uint32_t b0 = e0 + e1, b1 = e0 + e3, b2 = e1 + e3, b3 = e2 + e3;
+			uint32_t mn = b0;
+			if(b1 < mn) { mn = b1; ca = 1; }
+			if(b2 < mn) { mn = b2; ca = 2; }
+			if(b3 < mn) { mn = b3; ca = 3; }
+		}
+	}
+	int sidx0 = 0, sidx1 = 1;
+	if(CH == 2) {
+		sidx0 = (ca == 0 || ca == 1) ? 0 : (ca == 2 ? 3 : 2);
+		sidx1 = (ca == 0 || ca == 2) ? 1 : 3;
+	}
+	// this thread's channel / run
+	const int myc = (CH == 2 && tid >= TPC) ? 1 : 0;
+	const int run = tid - myc * TPC;
+	const SubframePlan *pl = bp + (myc ? sidx1 : sidx0);
+	const int type = __ldg(&pl->type), order = __ldg(&pl->order), wasted = __ldg(&pl->wasted), sbps = __ldg(&pl->bps);
+	const int po = __ldg(&pl->porder), method = __ldg(&pl->method), precision = __ldg(&pl->precision), shift = __ldg(&pl->shift);
+	const int wide = __ldg(&pl->wide);
+
+	// ---- frame header (stream_encoder_framing.c:245-391), built in registers by thread 0 while the copy is in flight:
+	// its content does not depend on anything the passes below compute, only its position does
+	const uint32_t gblk = P.blk0 + (uint32_t)blk;
+	const uint32_t frame_number = P.first_frame + (P.file_blocks ? gblk % (uint32_t)P.file_blocks : gblk);
+	uint32_t bs_code, bs_hint = 0, sr_code, sr_hint = 0;
+	switch(bs) {
+		case 192: bs_code = 1; break; case 576: bs_code = 2; break; case 1152: bs_code = 3; break;
+		case 2304: bs_code = 4; break; case 4608: bs_code = 5; break; case 256: bs_code = 8; break;
+		case 512: bs_code = 9; break; case 1024: bs_code = 10; break; case 2048: bs_code = 11; break;
+		case 4096: bs_code = 12; break; case 8192: bs_code = 13; break; case 16384: bs_code = 14; break;
+		case 32768: bs_code = 15; break;
+		default: bs_code = bs_hint = (bs <= 0x100) ? 6 : 7; break;
+	}
+	switch(P.sample_rate) {
+		case 88200: sr_code = 1; break; case 176400: sr_code = 2; break; case 192000: sr_code = 3; break;
+		case 8000: sr_code = 4; break; case 16000: sr_code = 5; break; case 22050: sr_code = 6; break;
+		case 24000: sr_code = 7; break; case 32000: sr_code = 8; break; case 44100: sr_code = 9; break;
+		case 48000: sr_code = 10; break; case 96000: sr_code = 11; break;
+		default:
+			if(P.sample_rate <= 255000 && P.sample_rate % 1000 == 0) sr_code = sr_hint = 12;
+			else if(P.sample_rate <= 655350 && P.sample_rate % 10 == 0) sr_code = sr_hint = 14;
+			else if(P.sample_rate <= 0xffff) sr_code = sr_hint = 13;
+			else sr_code = 0;
+			break;
+	}
+	uint32_t utf8_len;
+	if(frame_number < 0x80) utf8_len = 1;
+	else if(frame_number < 0x800) utf8_len = 2;
+	else if(frame_number < 0x10000) utf8_len = 3;
+	else if(frame_number < 0x200000) utf8_len = 4;
+	else if(frame_number < 0x4000000) utf8_len = 5;
+	else utf8_len = 6;
+	const uint32_t header_bits = 32 + 8 * utf8_len + (bs_hint ? (bs_hint == 6 ? 8 : 16) : 0) + (sr_hint ? (sr_hint == 12 ? 8 : 16) : 0) + 8;
+	uint32_t hdr[4] = {0, 0, 0, 0};  // header bytes, big-endian words, left aligned
+	if(tid == 0) {
+		uint32_t nb8 = 0, crc = 0;
+		auto push = [&](uint32_t byte) {
+			// append one byte (128-bit shift register) and run it through CRC-8, poly 0x07 (crc.c:39-76)
+			hdr[0] = (hdr[0] << 8) | (hdr[1] >> 24); hdr[1] = (hdr[1] << 8) | (hdr[2] >> 24);
+			hdr[2] = (hdr[2] << 8) | (hdr[3] >> 24); hdr[3] = (hdr[3] << 8) | (byte & 0xffu);
+			nb8++;
+			crc ^= byte & 0xffu;
+#pragma unroll
+			for(int j = 0; j < 8; j++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xffu : (crc << 1) & 0xffu;
+		};
+		uint32_t ca_code;
+		switch(ca) { case 0: ca_code = (uint32_t)P.channels - 1; break; case 1: ca_code = 8; break; case 2: ca_code = 9; break; default: ca_code = 10; break; }
+		uint32_t bps_code;
+		switch(P.bps) { case 8: bps_code = 1; break; case 12: bps_code = 2; break; case 16: bps_code = 4; break; case 20: bps_code = 5; break; case 24: bps_code = 6; break; case 32: bps_code = 7; break; default: bps_code = 0; break; }
+		push(0xff); push(0xf8);  // sync 0x3ffe, reserved 0, fixed-blocksize stream
+		push((bs_code << 4) | sr_code);
+		push((ca_code << 4) | (bps_code << 1));
+		const uint32_t v = frame_number;  // UTF-8 style frame number (bitwriter.c:832-933)
+		switch(utf8_len) {
+			case 1: push(v); break;
+			case 2: push(0xC0 | (v >> 6)); break;
+			case 3: push(0xE0 | (v >> 12)); break;
+			case 4: push(0xF0 | (v >> 18)); break;
+			case 5: push(0xF8 | (v >> 24)); break;
+			default: push(0xFC | (v >> 30)); break;
+		}
+		for(int kq = (int)utf8_len - 2; kq >= 0; kq--) push(0x80 | ((v >> (6 * kq)) & 0x3F));
+		if(bs_hint == 6) push((uint32_t)bs - 1);
+		else if(bs_hint == 7) { push(((uint32_t)bs - 1) >> 8); push((uint32_t)bs - 1); }
+		if(sr_hint == 12) push((uint32_t)P.sample_rate / 1000);
+		else if(sr_hint == 13) { push((uint32_t)P.sample_rate >> 8); push((uint32_t)P.sample_rate); }
+		else if(sr_hint == 14) { push(((uint32_t)P.sample_rate / 10) >> 8); push((uint32_t)P.sample_rate / 10); }
+		const uint32_t c8 = crc;
+		push(c8);
+		// left-align the nb8 bytes
+		for(uint32_t r = nb8; r < 16; r++) {
+			hdr[0] = (hdr[0] << 8) | (hdr[1] >> 24); hdr[1] = (hdr[1] << 8) | (hdr[2] >> 24);
+			hdr[2] = (hdr[2] << 8) | (hdr[3] >> 24); hdr[3] = hdr[3] << 8;
+		}
+	}
+
+	// ---- zero the word buffer up to an upper bound of the frame: a Rice partition's true length exceeds its
+	// estimate (count_rice_bits_in_partition_, stream_encoder.c:4929-4951) by at most n/2 + 1 bits
+	int zero_words;
+	{
+		unsigned long long bound = header_bits + 64;
+		bound += (unsigned long long)__ldg(&bp[sidx0].est_bits) + (unsigned)(bs >> 1) + (1u << kMaxPartitionOrder) + 64u;
+		if(CH == 2) bound += (unsigned long long)__ldg(&bp[sidx1].est_bits) + (unsigned)(bs >> 1) + (1u << kMaxPartitionOrder) + 64u;
+		unsigned long long zw = (bound >> 5) + 4;
+		if(zw > (unsigned long long)words_cap) zw = (unsigned long long)words_cap;
+		zero_words = (int)zw;
+		for(int i = tid; i < zero_words; i += NT) words[i] = 0;
+	}
+
+	// ---- pull the raw block into registers, then (after a barrier) write the planar signals over it
+	__syncthreads();  // mbarrier init visible to every waiter
+	mbar_wait(mbar, 0);
+	{
+		int4 rv[R_T / 4];
+#pragma unroll
+		for(int k = 0; k < R_T / 4; k++) rv[k] = *reinterpret_cast<const int4 *>(raw + 4 * (k * NT + tid));
+		__syncthreads();
+		int32_t *const p0 = planar + kSearch4ZeroRow;
+		int32_t *const p1 = planar + planar_words + kSearch4ZeroRow;
+		for(int i = tid; i < kSearch4ZeroRow; i += NT) { planar[i] = 0; if(CH == 2) planar[planar_words + i] = 0; }  // history of row 0
+		if(CH == 2) {
+			const int w0 = __ldg(&bp[sidx0].wasted), w1 = __ldg(&bp[sidx1].wasted);
+			auto pick = [](int s, int L, int R) -> int { return s == 0 ? L : s == 1 ? R : s == 2 ? ((L + R) >> 1) : (L - R); };
+#pragma unroll
+			for(int k = 0; k < R_T / 4; k++) {
+				const int i = 2 * (k * NT + tid);  // first of the two sample pairs in this vector
+				const int row = i / R_T, col = i - row * R_T;
+				*reinterpret_cast<int2 *>(p0 + row * 36 + col) = make_int2(pick(sidx0, rv[k].x, rv[k].y) >> w0, pick(sidx0, rv[k].z, rv[k].w) >> w0);
+				*reinterpret_cast<int2 *>(p1 + row * 36 + col) = make_int2(pick(sidx1, rv[k].x, rv[k].y) >> w1, pick(sidx1, rv[k].z, rv[k].w) >> w1);
+			}
+		}
+		else {
+#pragma unroll
+			for(int k = 0; k < R_T / 4; k++) {
+				const int i = 4 * (k * NT + tid);
+				const int row = i / R_T, col = i - row * R_T;
+				*reinterpret_cast<int4 *>(p0 + row * 36 + col) = make_int4(rv[k].x >> wasted, rv[k].y >> wasted, rv[k].z >> wasted, rv[k].w >> wasted);
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- pass 1: residual -> zig-zag (in place) -> bit count of this run
+	int32_t *const xs = planar + myc * planar_words + kSearch4ZeroRow;
+	int32_t *const rowp = xs + run * 36;
+	const int base = run * R_T;  // first sample of the run
+	const bool predicted = type == SF_FIXED || type == SF_LPC;
+	const int psize = bs >> po;
+	const uint32_t plen = method ? kRice2ParamLen : kRiceParamLen;
+	const bool one_partition = (psize % R_T) == 0;
+	uint32_t mybits = 0;
+	uint32_t k_run = 0;
+	if(run < FB200_MAX_LPC_ORDER) S.warm[myc][run] = xs[run];  // warm-up samples (all inside row 0: order <= 32 <= R_T)
+	if(predicted) {
+		int xg[MAXORD + G];
+		// history: the MAXORD samples before the run (previous row, or the zero row for run 0); loaded before ANY thread
+		// overwrites its row with zig-zagged residuals
+#pragma unroll
+		for(int k = 0; k < MAXORD / 4; k++) {
+			const int4 v = *reinterpret_cast<const int4 *>(rowp - MAXORD + 4 * k - ROWPAD);
+			xg[4 * k] = v.x; xg[4 * k + 1] = v.y; xg[4 * k + 2] = v.z; xg[4 * k + 3] = v.w;
+		}
+		__syncthreads();
+		int q[MAXORD];
+		if(type == SF_FIXED) {
+#pragma unroll
+			for(int j = 0; j < MAXORD; j++) q[j] = fixed_tap(order, j);
+		}
+		else {
+#pragma unroll
+			for(int j = 0; j < MAXORD; j++) q[j] = __ldg(&pl->qlp[j]);
+		}
+		const int qshift = type == SF_FIXED ? 0 : shift;
+		constexpr int NT12 = MAXORD < 12 ? MAXORD : 12;
+		const int cls = wide ? (order <= 8 ? 4 : 5) : (order <= 4 ? 0 : order <= 8 ? 1 : (MAXORD > 8 && order <= 12) ? 2 : 3);
+		int p = base / psize;
+		int next = (p + 1) * psize;
+		uint32_t k = __ldg(&pl->params[p]);
+		k_run = k;
+		uint32_t qsum = 0, ncoded = 0;
+#pragma unroll 1
+		for(int g = 0; g < NG; g++) {
+#pragma unroll
+			for(int kk = 0; kk < G / 4; kk++) {
+				const int4 v = *reinterpret_cast<const int4 *>(rowp + g * G + 4 * kk);
+				xg[MAXORD + 4 * kk] = v.x; xg[MAXORD + 4 * kk + 1] = v.y; xg[MAXORD + 4 * kk + 2] = v.z; xg[MAXORD + 4 * kk + 3] = v.w;
+			}
+			int r[G];
+			switch(cls) {
+				case 0: group_residual_narrow<G, MAXORD, 4>(xg, q, qshift, r); break;
+				case 1: group_residual_narrow<G, MAXORD, 8>(xg, q, qshift, r); break;
+				case 2: group_residual_narrow<G, MAXORD, NT12>(xg, q, qshift, r); break;
+				case 3: group_residual_narrow<G, MAXORD, MAXORD>(xg, q, qshift, r); break;
+				case 4: group_residual_wide<G, MAXORD, 8>(xg, q, qshift, r); break;
+				default: group_residual_wide<G, MAXORD, MAXORD>(xg, q, qshift, r); break;
+			}
+			uint32_t u[G];
+#pragma unroll
+			for(int m = 0; m < G; m++) u[m] = ((uint32_t)r[m] << 1) ^ (uint32_t)(r[m] >> 31);
+#pragma unroll
+			for(int kk = 0; kk < G / 4; kk++)
+				*reinterpret_cast<uint4 *>(rowp + g * G + 4 * kk) = make_uint4(u[4 * kk], u[4 * kk + 1], u[4 * kk + 2], u[4 * kk + 3]);
+			if(one_partition) {
+				if(base + g * G >= order) {
+#pragma unroll
+					for(int m = 0; m < G; m++) qsum += u[m] >> k;
+					ncoded += G;
+				}
+				else {
+#pragma unroll
+					for(int m = 0; m < G; m++)
+						if(base + g * G + m >= order) { qsum += u[m] >> k; ncoded++; }
+				}
+			}
+			else {
+#pragma unroll
+				for(int m = 0; m < G; m++) {
+					const int i = base + g * G + m;
+					if(i >= order) {
+						if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
+						if(i == p * psize || i == order) mybits += plen;
+						mybits += (u[m] >> k) + 1 + k;
+					}
+				}
+			}
+			// rotate: the last MAXORD samples just consumed become the history of the next group
+#pragma unroll
+			for(int j = 0; j < MAXORD; j++) xg[j] = xg[j + G];
+		}
+		if(one_partition) {
+			const int first_res = p == 0 ? order : p * psize;
+			mybits = qsum + ncoded * (k + 1) + ((first_res >= base && first_res < base + R_T) ? plen : 0u);
+		}
+	}
+	else {
+		__syncthreads();  // matches the barrier of the predicted branch (the type is per channel, barriers are per CTA)
+		if(type == SF_VERBATIM) mybits = (uint32_t)R_T * (uint32_t)sbps;
+	}
+	// bits in front of the first run of a channel: subframe header, warm-up, coefficients, entropy header
+	uint32_t pre = 0;
+	if(run == 0) {
+		pre = kSubframeHeaderBits + (uint32_t)wasted;
+		if(type == SF_CONSTANT) pre += (uint32_t)sbps;
+		else if(predicted) {
+			pre += (uint32_t)order * (uint32_t)sbps + kEntropyTypeLen + kRiceOrderLen;
+			if(type == SF_LPC) pre += kQlpPrecisionLen + kQlpShiftLen + (uint32_t)order * (uint32_t)precision;
+		}
+	}
+
+	// ---- ONE exclusive scan over all runs of the frame (channel 0's runs, then channel 1's)
+	uint32_t start, total;
+	{
+		const uint32_t v = mybits + pre;
+		uint32_t inc = v;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if(lane >= o) inc += t;
+		}
+		if(lane == 31) S.scan[warp] = inc;
+		__syncthreads();
+		const int nw = NT >> 5;
+		uint32_t wbase = 0, tot = 0;
+		for(int w = 0; w < nw; w++) {
+			const uint32_t s = S.scan[w];
+			if(w < warp) wbase += s;
+			tot += s;
+		}
+		start = header_bits + wbase + inc - v;  // first bit of `pre` (run 0) or of the run's residual codes
+		total = header_bits + tot;
+	}
+	const uint32_t nbytes = (total + 7) >> 3;      // frame bytes without the CRC-16
+	const uint32_t s0 = (4u - (nbytes & 3u)) & 3u;  // leading pad bytes: the frame's END is word aligned in `words`
+	const uint32_t bit0 = s0 * 8;
+	const uint32_t wend = (s0 + nbytes) >> 2;       // word index of the CRC-16
+	const bool fits = (int)wend + 2 <= zero_words;  // always, by the estimate's construction; fail loudly otherwise
+	// publish this frame's size for the frames behind it
+	if(tid == 0) {
+		st_volatile_u64(&A.lookback[blk], lb_pack(nbytes + 2, A.epoch, 1));
+		if(!fits) atomicExch(A.err, 2);
+	}
+
+	// ---- pass 2: pack
+	if(fits) {
+		if(tid == 0) {
+			// place the pre-built frame header at byte s0
+			const uint32_t sh = 8 * s0;
+			const uint32_t nwh = (header_bits >> 3) + 3 >> 2;
+			for(uint32_t i = 0; i <= nwh && i < 5; i++) {
+				const uint32_t hi = i > 0 ? hdr[i - 1] : 0u, lo = i < 4 ? hdr[i] : 0u;
+				const uint32_t w = sh ? __funnelshift_r(lo, hi, sh) : lo;  // bytes of hdr shifted right by s0
+				if(w) atomicOr(&words[i], w);
+			}
+		}
+		// subframe header fields: the first warp of a channel writes them, every field from its own lane
+		if(run < 32) {
+			const uint32_t sf0 = bit0 + __shfl_sync(0xffffffffu, start, 0);  // first bit of the subframe
+			const uint32_t warm0 = sf0 + kSubframeHeaderBits + (uint32_t)wasted;
+			const uint32_t after_warm = warm0 + (uint32_t)order * (uint32_t)sbps;
+			BitPut bw;
+			if(run == 0) {
+				uint32_t tb;
+				switch(type) {
+					case SF_CONSTANT: tb = 0x00; break;
+					case SF_VERBATIM: tb = 0x02; break;
+					case SF_FIXED: tb = 0x10 | ((uint32_t)order << 1); break;
+					default: tb = 0x40 | ((uint32_t)(order - 1) << 1); break;
+				}
+				bw.init(words, sf0);
+				bw.put(tb | (wasted ? 1u : 0u), 8);
+				if(wasted) { bw.skip((uint32_t)wasted - 1); bw.put(1, 1); }
+				if(type == SF_CONSTANT) bw.put(mask_bits(S.warm[myc][0], (uint32_t)sbps), (uint32_t)sbps);
+				bw.finish();
+				if(predicted) {
+					bw.init(words, after_warm);
+					if(type == SF_LPC) {
+						bw.put((uint32_t)precision - 1, kQlpPrecisionLen);
+						bw.put(mask_bits(shift, kQlpShiftLen), kQlpShiftLen);
+						bw.finish();
+						bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)order * (uint32_t)precision);
+					}
+					bw.put((uint32_t)method, kEntropyTypeLen);
+					bw.put((uint32_t)po, kRiceOrderLen);
+					bw.finish();
+				}
+			}
+			if(predicted) {
+				for(int i = run; i < order; i += 32) {
+					bw.init(words, warm0 + (uint32_t)i * (uint32_t)sbps);
+					bw.put(mask_bits(S.warm[myc][i], (uint32_t)sbps), (uint32_t)sbps);
+					bw.finish();
+				}
+				if(type == SF_LPC) {
+					for(int i = run; i < order; i += 32) {
+						bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)i * (uint32_t)precision);
+						bw.put(mask_bits(__ldg(&pl->qlp[i]), (uint32_t)precision), (uint32_t)precision);
+						bw.finish();
+					}
+				}
+			}
+		}
+		// residual codes of this run (stream_encoder_framing.c:538-594, bitwriter.c:575-706)
+		if(predicted) {
+			RunPacker pk;
+			pk.init(words, bit0 + start + pre);
+			if(one_partition) {
+				const uint32_t k = k_run;
+				const int pidx = base / psize;
+				const int first_res = pidx == 0 ? order : pidx * psize;
+				const uint32_t stop = 1u << k, lowmask = stop - 1u;
+#pragma unroll 1
+				for(int v4 = 0; v4 < R_T / 4; v4++) {
+					const uint4 uv = *reinterpret_cast<const uint4 *>(rowp + 4 * v4);
+					const uint32_t uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+					for(int e = 0; e < 4; e++) {
+						const int i = base + 4 * v4 + e;
+						if(i >= order) {
+							if(i == first_res) pk.put(k, plen);
+							const uint32_t qz = uu[e] >> k;
+							const uint32_t val = stop | (uu[e] & lowmask);
+							if(qz + k + 1 <= 32u) pk.put(val, qz + k + 1);  // zeros + stop bit + low bits as one field
+							else { pk.skip(qz); pk.put(val, k + 1); }
+						}
+					}
+				}
+			}
+			else {
+				int p = base / psize;
+				int next = (p + 1) * psize;
+				uint32_t k = __ldg(&pl->params[p]);
+#pragma unroll 1
+				for(int m = 0; m < R_T; m++) {
+					const int i = base + m;
+					if(i >= order) {
+						if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
+						if(i == p * psize || i == order) pk.put(k, plen);
+						const uint32_t u = (uint32_t)rowp[m];
+						pk.skip(u >> k);
+						pk.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
+					}
+				}
+			}
+			pk.finish();
+		}
+		else if(type == SF_VERBATIM) {
+			RunPacker pk;
+			pk.init(words, bit0 + start + pre);
+#pragma unroll 1
+			for(int m = 0; m < R_T; m++) pk.put(mask_bits(rowp[m], (uint32_t)sbps), (uint32_t)sbps);
+			pk.finish();
+		}
+	}
+	__syncthreads();
+
+	// ---- CRC-16 over the frame: equal word chunks aligned to the (word aligned) end, slicing-by-4, GF(2) combine.
+	// The signals are dead: the slicing tables go where they were.
+	for(int i = tid; i < 4 * 256 / 2; i += NT) reinterpret_cast<uint32_t *>(crc_tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.crc_tab) + i);
+	int Lw = ((int)wend + NT - 1) / NT;
+	Lw |= 1;  // odd chunk length: conflict-free strided reads
+	// level s of the combine tree multiplies by x^(32 Lw 2^s) (crc(A || B) = crc(A) x^|B| + crc(B), init 0)
+	if(tid < 9) {
+		uint32_t e = (32u * (uint32_t)Lw) << tid, m = 1;
+		for(int j = 0; e; j++, e >>= 1)
+			if(e & 1u) m = gf16_mul(m, kCrcXPow2[j % 15]);
+		S.mlev[tid] = m;
+	}
+	// the look-back runs here too (warp 1, or warp 0 of a one-warp CTA): its latency hides under the CRC pass
+	{
+		const int lbw = (NT > 32) ? 1 : 0;
+		if(warp == lbw) {
+			unsigned long long excl = 0;
+			int idx = blk - 1;
+			while(idx >= 0) {
+				const int j = idx - lane;
+				unsigned long long w;
+				unsigned flag;
+				do {
+					flag = 2;  // lanes in front of frame 0 stand for "inclusive prefix 0"
+					w = 0;
+					if(j >= 0) {
+						w = ld_volatile_u64(&A.lookback[j]);
+						flag = (((unsigned)(w >> 2)) & kLbEpochMask) == (A.epoch & kLbEpochMask) ? (unsigned)(w & 3u) : 0u;
+					}
+				} while(__any_sync(0xffffffffu, flag == 0));
+				const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2);
+				const int f = incl_mask ? __ffs((int)incl_mask) - 1 : 32;  // nearest predecessor that already holds an inclusive prefix
+				unsigned long long contrib = (lane <= f) ? (w >> 24) : 0ull;
+#pragma unroll
+				for(int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+				excl += contrib;
+				if(incl_mask) break;
+				idx -= 32;
+			}
+			if(lane == 0) {
+				st_volatile_u64(&A.lookback[blk], lb_pack(excl + nbytes + 2, A.epoch, 2));
+				const unsigned long long basebytes = *A.running_in;
+				S.off = basebytes + excl;
+				A.offsets[blk] = basebytes + excl;
+				if(blk == A.nb - 1) {
+					A.offsets[A.nb] = basebytes + excl + nbytes + 2;
+					*A.running_out = basebytes + excl + nbytes + 2;
+				}
+				if(A.chan_assign_out) A.chan_assign_out[blk] = (uint32_t)ca;
+			}
+		}
+	}
+	__syncthreads();
+	if(fits) {
+		const int cstart = (int)wend - (NT - tid) * Lw;
+		uint32_t crc = 0;
+		for(int w = cstart < 0 ? 0 : cstart; w < cstart + Lw; w++) {
+			const uint32_t x = words[w];
+			crc = (uint32_t)crc_tab[3 * 256 + (((crc >> 8) ^ (x >> 24)) & 0xffu)] ^ (uint32_t)crc_tab[2 * 256 + ((crc ^ (x >> 16)) & 0xffu)] ^
+			      (uint32_t)crc_tab[256 + ((x >> 8) & 0xffu)] ^ (uint32_t)crc_tab[x & 0xffu];
+		}
+#pragma unroll
+		for(int sl = 0; sl < 5; sl++) {
+			const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << sl);
+			crc = gf16_mul(crc, S.mlev[sl]) ^ other;  // meaningful in lanes that are multiples of 2 << sl; lane 0 is what counts
+		}
+		if(lane == 0) S.part[warp] = crc;
+	}
+	__syncthreads();
+	if(fits && warp == 0) {
+		const int nw = NT >> 5;
+		uint32_t crc = lane < nw ? S.part[lane] : 0;
+		for(int sl = 0; (1 << sl) < nw; sl++) {
+			const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << sl);
+			crc = gf16_mul(crc, S.mlev[5 + sl]) ^ other;
+		}
+		if(lane == 0) words[wend] = (words[wend] & 0xffffu) | (crc << 16);  // CRC-16, big-endian, right after the frame
+	}
+	__syncthreads();
+
+	// ---- copy the frame to its place in the stream (byte-granular destination alignment)
+	if(fits) {
+		const unsigned long long off = S.off;
+		const uint32_t totalb = nbytes + 2;
+		if(off + totalb > A.out_cap) {
+			if(tid == 0) atomicExch(A.err, 1);
+			return;
+		}
+		uint8_t *dst = A.out + off;
+		const uint32_t head = min(totalb, (uint32_t)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u));
+		auto frame_byte = [&](uint32_t j) -> uint8_t { const uint32_t bb = s0 + j; return (uint8_t)((words[bb >> 2] >> (24 - 8 * (bb & 3))) & 0xffu); };
+		if((uint32_t)tid < head) dst[tid] = frame_byte((uint32_t)tid);
+		const uint32_t nwd = (totalb - head) >> 2;
+		uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + head);
+		const uint32_t sb = s0 + head;  // shared-memory byte index of the first aligned destination word
+		const uint32_t wsrc = sb >> 2, sh = (sb & 3u) * 8u;
+		for(uint32_t i = tid; i < nwd; i += NT) {
+			const uint32_t be = sh ? __funnelshift_l(words[wsrc + i + 1], words[wsrc + i], sh) : words[wsrc + i];
+			d32[i] = __byte_perm(be, 0, 0x0123);
+		}
+		const uint32_t tail0 = head + nwd * 4;
+		if(tail0 + (uint32_t)tid < totalb) dst[tail0 + tid] = frame_byte(tail0 + (uint32_t)tid);
+	}
+}
+
+}  // namespace fb200

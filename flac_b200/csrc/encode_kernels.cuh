@@ -13,120 +13,68 @@
 // contraction: compile with -fmad=false); everything after quantisation is integer.
 #pragma once
 
-#include <cuda_runtime.h>
-#include <math_constants.h>
-#include <stdint.h>
-
-#include "fb200_internal.h"
-#include "glibc_log_data.h"
+#include "device_common.cuh"
 
 namespace fb200 {
-
-#ifndef M_LN2
-#define M_LN2 0.69314718055994530942
-#endif
-
-// ---------------------------------------------------------------- small helpers
-
-__device__ __forceinline__ uint32_t ilog2_u32(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
-__device__ __forceinline__ uint32_t ilog2_u64(uint64_t v) { return 63u - (uint32_t)__clzll((long long)v); }
-
-// bitmath.c:63-73 FLAC__bitmath_silog2
-__device__ __forceinline__ uint32_t silog2_i64(int64_t v)
-{
-	if(v == 0) return 0;
-	if(v == -1) return 2;
-	v = (v < 0) ? (-(v + 1)) : v;
-	return ilog2_u64((uint64_t)v) + 2;
-}
-
-__device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
-__device__ __forceinline__ uint32_t warp_and(uint32_t v) { return __reduce_and_sync(0xffffffffu, v); }
-
-__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v)
-{
-#pragma unroll
-	for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-	return v;
-}
-
-__device__ __forceinline__ uint32_t abs_u32(int32_t r) { return r < 0 ? (uint32_t)0 - (uint32_t)r : (uint32_t)r; }
-
-// ================================================================ log()
-// The reference calls the HOST libm's log() on its decision path (lpc.c:1594 order guess and
-// "don't even try" tests, fixed.c:284-288). CUDA's log() is not bit-identical to glibc's, so this is an
-// operation-by-operation restatement of the routine glibc selects on x86-64 hosts with FMA+AVX2
-// (`__log_fma`, the FMA build of sysdeps/ieee754/dbl-64/e_log.c), transcribed from its disassembly:
-// the same fused and unfused operations in the same order, tables extracted from the same binary
-// (glibc_log_data.h). tests/test_gpu_log.py compares it with the host's log() bit for bit.
-__device__ __forceinline__ double fb_log(double x)
-{
-	unsigned long long ix = (unsigned long long)__double_as_longlong(x);
-	if(ix - 0x3fee000000000000ull <= 0x308ffffffffffull) {
-		// 1 - 2^-4 <= x < 1 + 0x1.09p-4: polynomial in r = x - 1 with a double-double head
-		if(ix == 0x3ff0000000000000ull) return 0.0;
-		const double r = __dsub_rn(x, 1.0);
-		double p2 = __fma_rn(r, kLogB[2], kLogB[1]);
-		double p3 = __fma_rn(r, kLogB[5], kLogB[4]);
-		const double r2 = __dmul_rn(r, r);
-		double p5 = __fma_rn(r, kLogB[8], kLogB[7]);
-		p2 = __fma_rn(r2, kLogB[3], p2);
-		p3 = __fma_rn(r2, kLogB[6], p3);
-		const double r3 = __dmul_rn(r, r2);
-		double p1 = __fma_rn(r2, kLogB[9], p5);
-		p1 = __fma_rn(r3, kLogB[10], p1);
-		p1 = __fma_rn(p1, r3, p3);
-		p1 = __fma_rn(p1, r3, p2);
-		const double t = __fma_rn(r, 134217728.0, r);        // r + r*2^27
-		const double rhi = __fma_rn(-134217728.0, r, t);     // ... - r*2^27
-		const double b0 = kLogB[0];
-		const double rhi2 = __dmul_rn(rhi, rhi);
-		const double rlo = __dsub_rn(r, rhi);
-		const double hi = __fma_rn(rhi2, b0, r);
-		const double d = __dsub_rn(r, hi);
-		const double rs = __dadd_rn(r, rhi);
-		double lo = __fma_rn(rhi2, b0, d);
-		const double brlo = __dmul_rn(b0, rlo);
-		lo = __fma_rn(brlo, rs, lo);
-		const double y = __fma_rn(p1, r3, lo);
-		return __dadd_rn(hi, y);
-	}
-	const unsigned int top = (unsigned int)(ix >> 48);
-	if(top - 0x10u > 0x7fdfu) {
-		// x <= 0, subnormal, inf or nan
-		if((ix << 1) == 0) return -CUDART_INF;
-		if(ix == 0x7ff0000000000000ull) return x;
-		if((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return CUDART_NAN;
-		x = __dmul_rn(x, 4503599627370496.0);  // subnormal: scale by 2^52
-		ix = (unsigned long long)__double_as_longlong(x) - (52ull << 52);
-	}
-	const unsigned long long tmp = ix - 0x3fe6000000000000ull;
-	const int i = (int)((tmp >> 45) & 0x7f);
-	const int k = (int)((long long)tmp >> 52);
-	const unsigned long long iz = ix - (tmp & 0xfff0000000000000ull);
-	const double invc = kLogTab[2 * i], logc = kLogTab[2 * i + 1];
-	const double z = __longlong_as_double((long long)iz);
-	const double kd = (double)k;
-	const double w = __fma_rn(kd, kLogLn2Hi, logc);
-	const double r = __fma_rn(z, invc, -1.0);
-	const double q21 = __fma_rn(r, kLogA[2], kLogA[1]);
-	const double hi = __dadd_rn(r, w);
-	const double r2 = __dmul_rn(r, r);
-	double lo = __dsub_rn(w, hi);
-	lo = __dadd_rn(lo, r);
-	lo = __fma_rn(kd, kLogLn2Lo, lo);
-	const double r3 = __dmul_rn(r, r2);
-	double q = __fma_rn(r, kLogA[4], kLogA[3]);
-	lo = __fma_rn(r2, kLogA[0], lo);
-	q = __fma_rn(q, r2, q21);
-	const double y = __fma_rn(r3, q, lo);
-	return __dadd_rn(y, hi);
-}
 
 __global__ void k_debug_log(const double *__restrict__ x, double *__restrict__ y, int n)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i < n) y[i] = fb_log(x[i]);
+}
+
+// ================================================================ k_unpack
+// Packed little-endian signed PCM (2 or 3 bytes per sample, interleaved -- what a WAV/AIFF reader holds before the
+// reference's client widens it to int32, src/flac/encode.c:2352 format_input) -> the interleaved int32 layout of
+// FLAC__stream_encoder_process_interleaved. The only format-aware kernel: everything downstream sees int32.
+// Samples outside the stream's bits_per_sample set *err = 3 (the reference's process() range check,
+// stream_encoder.c:2543-2548).
+template <int BYTES>
+__global__ void __launch_bounds__(256) k_unpack(const uint8_t *__restrict__ packed, int32_t *__restrict__ pcm, unsigned long long n, int bps, int *__restrict__ err)
+{
+	// one thread = 4 consecutive samples: 8 (BYTES 2) or 12 (BYTES 3) input bytes -> one 16-byte store
+	const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long i0 = q * 4;
+	if(i0 >= n) return;
+	int v[4];
+	const uint8_t *src = packed + i0 * BYTES;
+	const bool full = i0 + 4 <= n;
+	if(full && (((uintptr_t)src) & 3) == 0) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(src);
+		if(BYTES == 2) {
+			const uint32_t a = __ldg(w), b = __ldg(w + 1);
+			v[0] = (int)(short)(a & 0xffffu); v[1] = (int)a >> 16; v[2] = (int)(short)(b & 0xffffu); v[3] = (int)b >> 16;
+		}
+		else {
+			const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+			v[0] = (int)(a << 8) >> 8;
+			v[1] = (int)(((a >> 24) | (b << 8)) << 8) >> 8;
+			v[2] = (int)(((b >> 16) | (c << 16)) << 8) >> 8;
+			v[3] = (int)c >> 8;
+		}
+	}
+	else {
+#pragma unroll
+		for(int e = 0; e < 4; e++) {
+			v[e] = 0;
+			if(i0 + e < n) {
+				const uint8_t *p = src + e * BYTES;
+				uint32_t u = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+				if(BYTES == 3) u |= (uint32_t)p[2] << 16;
+				v[e] = (int)(u << (32 - 8 * BYTES)) >> (32 - 8 * BYTES);
+			}
+		}
+	}
+	bool bad = false;
+#pragma unroll
+	for(int e = 0; e < 4; e++) {
+		const int t = v[e] >> (bps - 1);
+		bad |= (t != 0 && t != -1);
+	}
+	if(bad && bps < 8 * BYTES) atomicExch(err, 3);
+	if(full) *reinterpret_cast<int4 *>(pcm + i0) = make_int4(v[0], v[1], v[2], v[3]);
+	else
+		for(int e = 0; e < 4 && i0 + e < n; e++) pcm[i0 + e] = v[e];
 }
 
 // ================================================================ k_prep
@@ -471,14 +419,6 @@ struct SearchShared {
 	int c_qlp[FB200_MAX_LPC_ORDER];
 };
 
-// stream_encoder.c:4929-4951 count_rice_bits_in_partition_
-__device__ __forceinline__ uint32_t count_rice_bits(uint32_t k, uint32_t partition_samples, uint64_t abs_sum)
-{
-	const uint64_t v = (uint64_t)kRiceParamLen + (uint64_t)(1 + k) * partition_samples +
-	                   (k ? (abs_sum >> (k - 1)) : (abs_sum << 1)) - (partition_samples >> 1);
-	return (uint32_t)(v < 0xffffffffull ? v : 0xffffffffull);
-}
-
 // Evaluate one predictor on the block in shared memory and, if it beats the best-so-far
 // (strict '<', stream_encoder.c:4191-4194, 4265-4269), record it. type: SF_FIXED or SF_LPC.
 __device__ void evaluate_candidate(const EncK &P, SearchShared &S, const int32_t *__restrict__ x, uint32_t *__restrict__ absr,
@@ -733,67 +673,6 @@ __global__ void __launch_bounds__(128) k_search(EncK P, const int32_t *__restric
 // the last word of a run can be shared with a neighbour -> atomicOr), then CRC-16 is
 // computed in parallel by chunk + GF(2) combine, and the frame is copied to its slot.
 
-struct BitPut {
-	uint32_t *words;
-	uint32_t cur;
-	uint32_t pos;
-	int widx, first;
-	__device__ __forceinline__ void init(uint32_t *w, uint32_t bitpos)
-	{
-		words = w; pos = bitpos; widx = (int)(bitpos >> 5); first = widx; cur = 0;
-	}
-	__device__ __forceinline__ void flush()
-	{
-		if(cur) {
-			if(widx == first) atomicOr(&words[widx], cur);
-			else words[widx] = cur;  // interior word: exclusively ours, buffer pre-zeroed
-		}
-		cur = 0;
-	}
-	__device__ __forceinline__ void skip(uint32_t n)  // n zero bits
-	{
-		pos += n;
-		const int nw = (int)(pos >> 5);
-		if(nw != widx) { flush(); widx = nw; }
-	}
-	__device__ __forceinline__ void put(uint32_t value, uint32_t nbits)  // 1..32 bits, value < 2^nbits
-	{
-		const uint32_t off = pos & 31u;
-		const unsigned long long v = (unsigned long long)value << (64u - off - nbits);
-		cur |= (uint32_t)(v >> 32);
-		pos += nbits;
-		if(off + nbits >= 32u) {
-			flush();
-			widx++;
-			cur = (uint32_t)v;
-		}
-	}
-	__device__ __forceinline__ void finish()
-	{
-		if(cur) atomicOr(&words[widx], cur);  // last (partial) word may be shared
-		cur = 0;
-	}
-};
-
-__device__ __forceinline__ uint32_t mask_bits(int32_t v, uint32_t n) { return n >= 32 ? (uint32_t)v : ((uint32_t)v & ((1u << n) - 1u)); }
-__device__ __forceinline__ int skew(int i) { return i + (i >> 5); }  // bank-conflict-free run access
-
-// GF(2)[x] multiply mod x^16+x^15+x^2+1 (CRC-16 poly 0x8005, crc.c:78)
-__device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b)
-{
-	uint32_t r = 0;
-#pragma unroll
-	for(int i = 15; i >= 0; i--) {
-		r = (r & 0x8000u) ? ((r << 1) ^ 0x8005u) & 0xffffu : (r << 1);
-		if((b >> i) & 1u) r ^= a;
-	}
-	return r;
-}
-
-// x^(2^j) mod (x^16+x^15+x^2+1) for j = 0..14 (x has order 32767, so x^(2^15) = x and the table is periodic);
-// generated with gf16_mul by repeated squaring from x = 0x2.
-__device__ __constant__ const uint16_t kCrcXPow2[15] = {0x2, 0x4, 0x10, 0x100, 0x8005, 0x8017, 0x8113, 0x106, 0x8011, 0x8107, 0x16, 0x114, 0x8115, 0x112, 0x8101};
-
 // block-wide exclusive scan for 256 threads; returns exclusive prefix, *total = sum
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_warp /*[9]*/, uint32_t *total)
 {
@@ -867,7 +746,8 @@ __global__ void __launch_bounds__(256) k_emit(EncK P, const int32_t *__restrict_
 	}
 	__syncthreads();
 	const int ca = s_ca;
-	const uint32_t frame_number = P.first_frame + (uint32_t)blk;
+	const uint32_t gblk = P.blk0 + (uint32_t)blk;
+	const uint32_t frame_number = P.first_frame + (P.file_blocks ? gblk % (uint32_t)P.file_blocks : gblk);
 
 	// ---- frame header (stream_encoder_framing.c:245-391), thread 0
 	uint32_t bs_code, bs_hint = 0, sr_code, sr_hint = 0;

@@ -14,9 +14,7 @@
 #include <map>
 #include <vector>
 
-#include "encode_kernels_v3.cuh"
-#include "autoc_kernel.cuh"
-#include "search_kernel.cuh"
+#include "fb200_internal.h"
 #include "windows.h"
 
 namespace fb200 {
@@ -37,13 +35,12 @@ struct Geometry {
 	float *d_windows = nullptr;
 	DevSection *d_secs = nullptr;
 	DevCand *d_cands = nullptr;
-	size_t search_smem = 0, emit_smem = 0;
-	size_t search2_smem = 0, emit2_smem = 0;
-	int fast_search3 = 0;       // 0, or R_T (32/36) of the warp-per-signal kernel
-	size_t search3_smem = 0;
+	size_t search_smem = 0, emit_smem = 0;  // general kernels
+	int fast_search3 = 0;       // 0, or R_T (32/36) of the warp-per-signal search kernel (k_search4)
 	size_t search4_smem = 0;
-	int fast_search = 0, fast_emit = 0;  // 0 = general kernels; emit: 256 / 128 = CTA width of the fast kernel
 	int maxord_t = 8;
+	int emit3_rt = 0;           // 0, or R_T of the resident emit kernel (k_emit3)
+	size_t emit3_smem = 0;
 };
 
 }  // namespace fb200
@@ -66,8 +63,16 @@ struct fb200_encoder {
 	uint8_t *d_slots = nullptr;
 	uint32_t *d_frame_bytes = nullptr;
 	uint32_t *d_chan_assign = nullptr;
-	unsigned long long *d_running = nullptr;
+	unsigned long long *d_running = nullptr;  // [2]: k_emit3 reads [run_cur] and writes [run_cur ^ 1]; k_scan updates [run_cur] in place
+	int run_cur = 0;
 	int *d_err = nullptr;
+	// k_emit3: slicing tables, look-back status words, frame tickets
+	uint16_t *d_crc_tab = nullptr;
+	unsigned long long *d_lookback = nullptr;
+	unsigned *d_ticket = nullptr;
+	unsigned ticket_base = 0, epoch = 0;
+	uint32_t file_blocks = 0;
+
 	size_t max_nsec = 0, max_nslots = 0, lag_stride = 0;
 	// stage-A outputs are double-buffered so that stage A (prep/autoc/lpc) of sub-batch i+1 can run on
 	// s_a concurrently with stage B (search/emit/scan/gather) of sub-batch i on the caller's stream
@@ -78,6 +83,8 @@ struct fb200_encoder {
 	// staging for the host entry point
 	int32_t *d_pcm = nullptr;
 	size_t d_pcm_cap = 0;
+	uint8_t *d_packed = nullptr;  // packed 16-/24-bit input of fb200_encode_host_packed
+	size_t d_packed_cap = 0;
 	uint8_t *d_out = nullptr;
 	size_t d_out_cap = 0;
 	unsigned long long *d_offsets = nullptr;
@@ -87,11 +94,8 @@ struct fb200_encoder {
 	unsigned long long *h_totals = nullptr;  // pinned
 	size_t h_totals_cap = 0;
 	uint64_t launches = 0;
-	bool autoc_split = false;
 	int host_chunks = 12;   // chunks per fb200_encode_host call (FB200_HOST_CHUNKS): copy/compute overlap granularity; measured best 8-12 (tools/sweep_host_chunks.py)
 	int pipe_chunks = 1;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS); see fb200_encode_device
-	int autoc_version = 3;  // FB200_AUTOC_KERNEL=2 selects the thread-private-load generation (k_autoc2)
-	int search_version = 4;  // FB200_SEARCH_KERNEL=1|2|3|4 selects the search kernel generation (benchmarks/tests)
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
 	bool prof_on = false;
@@ -215,121 +219,26 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 	{
 		const int xcap = k.bs_stride + (k.bs_stride >> 5) + 1;
 		g.emit_smem = (size_t)xcap * 8 + (size_t)k.slot_words * 4;
-	}
-	{
-		// fast-path eligibility (encode_kernels_v2.cuh)
-		const int xcap = k.bs_stride + (k.bs_stride >> 5) + 1;
 		g.maxord_t = k.max_order <= 8 ? 8 : k.max_order <= 12 ? 12 : 32;
-		g.fast_search = (bs % 128 == 0 && bs / 128 <= 36 && k.max_po <= 7) ? 1 : 0;
-		if(bs % 256 == 0 && bs / 256 <= 18) g.fast_emit = 256;
-		else if(bs % 128 == 0 && bs / 128 <= 36) g.fast_emit = 128;
 		{
 			int rt = 0;
 			if(bs % (32 * 32) == 0) rt = 32;
 			else if(bs % (32 * 36) == 0) rt = 36;
-			const size_t per_warp = rt ? (((size_t)(bs / rt) * 36 * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared) + 15) / 16 * 16) : 0;
 			const int ntl = rt ? bs / (32 * rt) : 0;  // tiles; the partition <-> lane mapping needs a power of two
-			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * per_warp <= 110 * 1024) {
+			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * search4_bytes_per_warp(bs, rt) <= 110 * 1024) {
 				g.fast_search3 = rt;
-				g.search3_smem = 2 * per_warp;
 				g.search4_smem = 2 * search4_bytes_per_warp(bs, rt);
 			}
 		}
-		g.search2_smem = (size_t)xcap * 4;
-		g.emit2_smem = (size_t)xcap * 4 + (size_t)k.slot_words * 4;
+		// resident emit kernel: 1-2 channels, runs of R_T samples, one thread per run, at most 256 threads
+		if(g.fast_search3 && k.channels <= 2 && (bs / g.fast_search3) >= 32 && (bs / g.fast_search3) * k.channels <= 256 && ((size_t)bs * k.channels * 4) % 16 == 0) {
+			const size_t need = emit3_smem_bytes(bs, g.fast_search3, k.channels, k.slot_words);
+			if(need <= 200 * 1024) { g.emit3_rt = g.fast_search3; g.emit3_smem = need; }
+		}
 	}
 	e->geoms[bs] = g;
 	*out = &e->geoms[bs];
 	return FB200_OK;
-}
-
-template <int LAGS>
-static void launch_autoc(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
-{
-	const int total = nitems * k.nsec;
-	k_autoc<LAGS><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
-}
-
-template <int NACC, int SPLIT, int U>
-static void launch_autoc2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
-{
-	const int total = nitems * k.nsec * SPLIT;
-	k_autoc2<NACC, SPLIT, U><<<(total + 127) / 128, 128, 0, st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
-}
-
-template <int LAGS, int U, int K, int STAGES>
-static void launch_autoc3(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
-{
-	const int groups = (nitems + 31) / 32;
-	k_autoc3<LAGS, U, K, STAGES><<<groups * k.nsec, 32, autoc3_smem_bytes<LAGS, U, K, STAGES>(), st>>>(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems);
-}
-
-template <int MO>
-static void launch_search2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
-{
-	if(k.bs / 128 == 32) k_search2<32, MO, true><<<nitems, 128, g.search2_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
-	else k_search2<36, MO, false><<<nitems, 128, g.search2_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
-}
-
-template <int MO>
-static void launch_search3(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
-{
-	const int grid = (nitems + 1) / 2;
-	const bool widek = k.bps > 16;
-	if(g.fast_search3 == 32) {
-		if(widek) k_search3<32, MO, 2, true><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-		else k_search3<32, MO, 2, false><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-	}
-	else {
-		if(widek) k_search3<36, MO, 2, true><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-		else k_search3<36, MO, 2, false><<<grid, 64, g.search3_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-	}
-}
-
-template <int MO>
-static void launch_search4(const EncK &k, const fb200_encoder *e, const Geometry &g, int nitems, cudaStream_t st)
-{
-	const int grid = (nitems + 1) / 2;
-	const bool widek = k.bps > 16;
-	if(g.fast_search3 == 32) {
-		if(widek) k_search4<32, MO, 2, true><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-		else k_search4<32, MO, 2, false><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-	}
-	else {
-		if(widek) k_search4<36, MO, 2, true><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-		else k_search4<36, MO, 2, false><<<grid, 64, g.search4_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems);
-	}
-}
-
-template <int MO>
-static void launch_emit2(const EncK &k, const fb200_encoder *e, const Geometry &g, int nb, cudaStream_t st)
-{
-	if(g.fast_emit == 256) {
-		if(k.bs / 256 == 16) k_emit2<256, 16, MO, true><<<nb, 256, g.emit2_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
-		else k_emit2<256, 18, MO, false><<<nb, 256, g.emit2_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
-	}
-	else k_emit2<128, 36, MO, false><<<nb, 128, g.emit2_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
-}
-
-template <int MO>
-static void set_smem_attrs(int search_bytes, int emit_bytes)
-{
-	cudaFuncSetAttribute(k_search3<32, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search3<36, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search3<32, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search3<36, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	{
-		constexpr int MO4 = MO;
-		cudaFuncSetAttribute(k_search4<32, MO4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-		cudaFuncSetAttribute(k_search4<36, MO4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-		cudaFuncSetAttribute(k_search4<32, MO4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-		cudaFuncSetAttribute(k_search4<36, MO4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	}
-	cudaFuncSetAttribute(k_search2<32, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
-	cudaFuncSetAttribute(k_search2<36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, search_bytes);
-	cudaFuncSetAttribute(k_emit2<256, 16, MO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
-	cudaFuncSetAttribute(k_emit2<256, 18, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
-	cudaFuncSetAttribute(k_emit2<128, 36, MO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_bytes);
 }
 
 static void use_ws(fb200_encoder *e, int b)
@@ -344,46 +253,14 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	EncK k = g.k;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
-	k_prep<<<nb, 256, 0, st>>>(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags);
+	launch_prep(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags, nb, st);
 	prof_mark(e, FB200_PROF_PREP, st);
 	e->launches++;
 	if(k.nwin > 0) {
-		if(e->use_v1) {
-			if(k.lags <= 7) launch_autoc<7>(k, e, g, nitems, st);
-			else if(k.lags <= 9) launch_autoc<9>(k, e, g, nitems, st);
-			else if(k.lags <= 13) launch_autoc<13>(k, e, g, nitems, st);
-			else if(k.lags <= 17) launch_autoc<17>(k, e, g, nitems, st);
-			else launch_autoc<33>(k, e, g, nitems, st);
-		}
-		else {
-			// one thread per chain (splitting the lags over two threads was measured slower: the sample
-			// stream conversion is paid twice); FB200_AUTOC_SPLIT=1 keeps the split variant selectable
-			if(e->autoc_version == 3) {
-				// warp per 32 chains, cp.async-staged tiles (autoc_kernel.cuh)
-				if(k.lags <= 7) launch_autoc3<7, 28, 2, 4>(k, e, g, nitems, st);
-				else if(k.lags <= 9) launch_autoc3<9, 36, 2, 4>(k, e, g, nitems, st);
-				else if(k.lags <= 13) launch_autoc3<13, 52, 1, 4>(k, e, g, nitems, st);
-				else if(k.lags <= 17) launch_autoc3<17, 68, 1, 3>(k, e, g, nitems, st);
-				else launch_autoc3<33, 132, 1, 3>(k, e, g, nitems, st);
-			}
-			else if(e->autoc_split) {
-				if(k.lags <= 7) launch_autoc2<4, 2, 8>(k, e, g, nitems, st);
-				else if(k.lags <= 9) launch_autoc2<5, 2, 20>(k, e, g, nitems, st);
-				else if(k.lags <= 13) launch_autoc2<7, 2, 28>(k, e, g, nitems, st);
-				else if(k.lags <= 17) launch_autoc2<9, 2, 36>(k, e, g, nitems, st);
-				else launch_autoc2<17, 2, 68>(k, e, g, nitems, st);
-			}
-			else {
-				if(k.lags <= 7) launch_autoc2<7, 1, 28>(k, e, g, nitems, st);
-				else if(k.lags <= 9) launch_autoc2<9, 1, 36>(k, e, g, nitems, st);
-				else if(k.lags <= 13) launch_autoc2<13, 1, 52>(k, e, g, nitems, st);
-				else if(k.lags <= 17) launch_autoc2<17, 1, 68>(k, e, g, nitems, st);
-				else launch_autoc2<33, 1, 132>(k, e, g, nitems, st);
-			}
-		}
+		if(e->use_v1) launch_autoc_general(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
+		else launch_autoc3(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		prof_mark(e, FB200_PROF_AUTOC, st);
-		const int total = nitems * k.nwin;
-		k_lpc<<<(total + 127) / 128, 128, 0, st>>>(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems);
+		launch_lpc(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems, st);
 		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
@@ -391,46 +268,46 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	return FB200_OK;
 }
 
-// Stage B: k_search, k_emit, k_scan, k_gather (reads the current workspace set).
-static int run_stage_b(fb200_encoder *e, Geometry &g, int nb, uint32_t first_frame, uint64_t frame_index0,
+// Stage B: search + emit (reads the current workspace set). Regular blocksizes: k_search4 + k_emit3 (frames go straight
+// to their final offsets); everything else: the general k_search + k_emit + k_scan + k_gather.
+static int run_stage_b(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int nb, uint32_t first_frame, uint64_t frame_index0,
                        uint8_t *d_out, size_t out_cap, unsigned long long *d_offsets, cudaStream_t st)
 {
 	EncK k = g.k;
 	k.first_frame = first_frame;
+	k.blk0 = (uint32_t)frame_index0;
+	k.file_blocks = (int)e->file_blocks;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
-	if(g.fast_search3 && !e->use_v1 && e->search_version >= 4) {
-		// orders above 12 (non-preset -l 13..32) stay on k_search3: k_search4's 32-tap instantiation mis-evaluates
-		// orders > 16 (found by tests/test_gpu_encode.py::test_option_matrix; not yet root-caused)
-		if(g.maxord_t == 8) launch_search4<8>(k, e, g, nitems, st);
-		else if(g.maxord_t == 12) launch_search4<12>(k, e, g, nitems, st);
-		else if(e->search_version >= 5) launch_search4<32>(k, e, g, nitems, st);  // FB200_SEARCH_KERNEL=5: experimental, see above
-		else launch_search3<32>(k, e, g, nitems, st);
-	}
-	else if(g.fast_search3 && !e->use_v1 && e->search_version >= 3) {
-		if(g.maxord_t == 8) launch_search3<8>(k, e, g, nitems, st);
-		else if(g.maxord_t == 12) launch_search3<12>(k, e, g, nitems, st);
-		else launch_search3<32>(k, e, g, nitems, st);
-	}
-	else if(g.fast_search && !e->use_v1 && e->search_version >= 2) {
-		if(g.maxord_t == 8) launch_search2<8>(k, e, g, nitems, st);
-		else if(g.maxord_t == 12) launch_search2<12>(k, e, g, nitems, st);
-		else launch_search2<32>(k, e, g, nitems, st);
-	}
-	else k_search<<<nitems, 128, g.search_smem, st>>>(k, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans);
+	if(g.fast_search3 && !e->use_v1) launch_search4(k, g.fast_search3, g.maxord_t, g.search4_smem, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems, st);
+	else launch_search_general(k, g.search_smem, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems, st);
 	prof_mark(e, FB200_PROF_SEARCH, st);
-	if(g.fast_emit && !e->use_v1) {
-		if(g.maxord_t == 8) launch_emit2<8>(k, e, g, nb, st);
-		else if(g.maxord_t == 12) launch_emit2<12>(k, e, g, nb, st);
-		else launch_emit2<32>(k, e, g, nb, st);
+	if(g.emit3_rt && !e->use_v1 && ((uintptr_t)d_pcm & 15) == 0) {
+		if((++e->epoch & kLbEpochMask) == 0) {
+			FB_CUDA(cudaMemsetAsync(e->d_lookback, 0, (size_t)e->max_blocks * sizeof(unsigned long long), st));
+			e->epoch = 1;
+		}
+		Emit3Args a;
+		a.pcm = d_pcm; a.meta = e->d_meta; a.blkflags = e->d_blkflags; a.plans = e->d_plans; a.crc_tab = e->d_crc_tab;
+		a.out = d_out; a.out_cap = (unsigned long long)out_cap; a.offsets = d_offsets + frame_index0;
+		a.running_in = e->d_running + e->run_cur; a.running_out = e->d_running + (e->run_cur ^ 1);
+		a.lookback = e->d_lookback; a.ticket = e->d_ticket; a.ticket_base = e->ticket_base; a.epoch = e->epoch;
+		a.nb = nb; a.chan_assign_out = e->d_chan_assign; a.err = e->d_err;
+		launch_emit3(k, g.emit3_rt, g.maxord_t, g.emit3_smem, a, nb, st);
+		e->ticket_base += (unsigned)nb;
+		e->run_cur ^= 1;
+		prof_mark(e, FB200_PROF_EMIT, st);
+		e->launches += 2;
 	}
-	else k_emit<<<nb, 256, g.emit_smem, st>>>(k, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign);
-	prof_mark(e, FB200_PROF_EMIT, st);
-	k_scan<<<1, 1024, 0, st>>>(e->d_frame_bytes, nb, d_offsets + frame_index0, e->d_running);
-	prof_mark(e, FB200_PROF_SCAN, st);
-	k_gather<<<nb, 256, 0, st>>>(k, e->d_slots, e->d_frame_bytes, d_offsets + frame_index0, d_out, (unsigned long long)out_cap, e->d_err);
-	prof_mark(e, FB200_PROF_GATHER, st);
-	e->launches += 4;
+	else {
+		launch_emit_general(k, g.emit_smem, e->d_sig, e->d_blkflags, e->d_plans, e->d_slots, e->d_frame_bytes, e->d_chan_assign, nb, st);
+		prof_mark(e, FB200_PROF_EMIT, st);
+		launch_scan(e->d_frame_bytes, nb, d_offsets + frame_index0, e->d_running + e->run_cur, st);
+		prof_mark(e, FB200_PROF_SCAN, st);
+		launch_gather(k, e->d_slots, e->d_frame_bytes, d_offsets + frame_index0, d_out, (unsigned long long)out_cap, e->d_err, nb, st);
+		prof_mark(e, FB200_PROF_GATHER, st);
+		e->launches += 4;
+	}
 	FB_CUDA(cudaGetLastError());
 	return FB200_OK;
 }
@@ -452,7 +329,7 @@ static int enqueue_chunk(fb200_encoder *e, size_t idx, const PipeChunk &c, const
 	if((rc = run_stage_a(e, *g, d_pcm_base + (size_t)c.first * bs * ch, (int)c.nb, e->s_a)) != FB200_OK) return rc;
 	FB_CUDA(cudaEventRecord(e->ev_a[b], e->s_a));
 	FB_CUDA(cudaStreamWaitEvent(sb, e->ev_a[b], 0));
-	if((rc = run_stage_b(e, *g, (int)c.nb, first_frame_number + (uint32_t)c.first, c.first, d_out, out_cap, d_offsets, sb)) != FB200_OK) return rc;
+	if((rc = run_stage_b(e, *g, d_pcm_base + (size_t)c.first * bs * ch, (int)c.nb, first_frame_number, c.first, d_out, out_cap, d_offsets, sb)) != FB200_OK) return rc;
 	FB_CUDA(cudaEventRecord(e->ev_b[b], sb));
 	e->ev_b_valid[b] = true;
 	return FB200_OK;
@@ -676,7 +553,10 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	ALLOC(e->d_slots, nb * slot);
 	ALLOC(e->d_frame_bytes, nb * sizeof(uint32_t));
 	ALLOC(e->d_chan_assign, nb * sizeof(uint32_t));
-	ALLOC(e->d_running, sizeof(unsigned long long));
+	ALLOC(e->d_running, 2 * sizeof(unsigned long long));
+	ALLOC(e->d_crc_tab, 4 * 256 * sizeof(uint16_t));
+	ALLOC(e->d_lookback, nb * sizeof(unsigned long long));
+	ALLOC(e->d_ticket, sizeof(unsigned));
 	ALLOC(e->d_err, sizeof(int));
 #undef ALLOC
 	if(cudaStreamCreateWithFlags(&e->s_a, cudaStreamNonBlocking) != cudaSuccess ||
@@ -688,37 +568,43 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 		fb200_encoder_destroy(e);
 		return FB200_ERR_CUDA;
 	}
-	// shared memory opt-in for the two big kernels
+	cudaMemset(e->d_lookback, 0, nb * sizeof(unsigned long long));
+	cudaMemset(e->d_ticket, 0, sizeof(unsigned));
+	launch_crc16_tables(e->d_crc_tab, 0);
 	Geometry *g = nullptr;
 	int rc = build_geometry(e, (int)c.blocksize, &g);
 	if(rc != FB200_OK) { fb200_encoder_destroy(e); return rc; }
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties(&prop, device);
-	if(g->search_smem + 8192 > prop.sharedMemPerBlockOptin || g->emit_smem + 4096 > prop.sharedMemPerBlockOptin) {
+	if(!g->fast_search3 && (g->search_smem + 8192 > prop.sharedMemPerBlockOptin || g->emit_smem + 4096 > prop.sharedMemPerBlockOptin)) {
 		set_error("blocksize %u x %u channels needs more shared memory than the device offers (search %zu, emit %zu)", c.blocksize, c.channels, g->search_smem, g->emit_smem);
 		fb200_encoder_destroy(e);
 		return FB200_ERR_UNSUPPORTED;
 	}
-	cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->search_smem);
-	cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->emit_smem);
-	set_smem_attrs<8>((int)g->search2_smem, (int)g->emit2_smem);
-	set_smem_attrs<12>((int)g->search2_smem, (int)g->emit2_smem);
-	set_smem_attrs<32>((int)g->search2_smem, (int)g->emit2_smem);
+	if(!g->emit3_rt && g->emit_smem + 4096 > prop.sharedMemPerBlockOptin) {
+		set_error("blocksize %u x %u channels: a frame does not fit shared memory (emit %zu)", c.blocksize, c.channels, g->emit_smem);
+		fb200_encoder_destroy(e);
+		return FB200_ERR_UNSUPPORTED;
+	}
+	{
+		// dynamic shared-memory opt-ins are per function and per device: raised once to fixed maxima, never per encoder
+		// (two encoders with different blocksizes in one process must not lower each other's limit)
+		static bool inited[64] = {false};
+		if(device < 64 && !inited[device]) {
+			general_kernels_init(device);
+			autoc3_init(device);
+			search4_init(device);
+			emit3_init(device);
+			inited[device] = true;
+		}
+	}
 	{
 		const char *env = getenv("FB200_FORCE_GENERAL_KERNELS");
 		e->use_v1 = env && env[0] == '1';
-		const char *as = getenv("FB200_AUTOC_SPLIT");
-		e->autoc_split = as && as[0] == '1';
-		const char *pc = getenv("FB200_PIPE_CHUNKS");
-		if(pc && atoi(pc) >= 1 && atoi(pc) <= 64) e->pipe_chunks = atoi(pc);
 		const char *hc = getenv("FB200_HOST_CHUNKS");
 		if(hc && atoi(hc) >= 1 && atoi(hc) <= 256) e->host_chunks = atoi(hc);
-		const char *av = getenv("FB200_AUTOC_KERNEL");
-		if(av && (av[0] == '2' || av[0] == '3')) e->autoc_version = av[0] - '0';
-		if(e->autoc_split) e->autoc_version = 2;
-		cudaFuncSetAttribute(k_autoc3<33, 132, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoc3_smem_bytes<33, 132, 1, 3>());
-		const char *sv = getenv("FB200_SEARCH_KERNEL");
-		if(sv && sv[0] >= '1' && sv[0] <= '5') e->search_version = sv[0] - '0';
+		const char *pc = getenv("FB200_PIPE_CHUNKS");
+		if(pc && atoi(pc) >= 1 && atoi(pc) <= 64) e->pipe_chunks = atoi(pc);
 	}
 	*out = e;
 	return FB200_OK;
@@ -740,7 +626,8 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	if(e->s_a) cudaStreamDestroy(e->s_a);
 	cudaFree(e->d_plans); cudaFree(e->d_slots); cudaFree(e->d_frame_bytes); cudaFree(e->d_chan_assign);
 	cudaFree(e->d_running); cudaFree(e->d_err);
-	cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_offsets);
+	cudaFree(e->d_crc_tab); cudaFree(e->d_lookback); cudaFree(e->d_ticket);
+	cudaFree(e->d_pcm); cudaFree(e->d_packed); cudaFree(e->d_out); cudaFree(e->d_offsets);
 	if(e->stream) cudaStreamDestroy(e->stream);
 	if(e->s_h2d) cudaStreamDestroy(e->s_h2d);
 	if(e->s_d2h) cudaStreamDestroy(e->s_d2h);
@@ -772,7 +659,7 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 	const uint64_t nfull = samples / bs;
 	const uint32_t tail = (uint32_t)(samples % bs);
 	if(nframes) *nframes = (uint32_t)(nfull + (tail ? 1 : 0));
-	FB_CUDA(cudaMemsetAsync(e->d_running, 0, sizeof(unsigned long long), st));
+	FB_CUDA(cudaMemsetAsync(e->d_running, 0, 2 * sizeof(unsigned long long), st));
 	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), st));
 	unsigned long long *offs = reinterpret_cast<unsigned long long *>(d_frame_offsets);
 	if(samples == 0) FB_CUDA(cudaMemsetAsync(offs, 0, sizeof(unsigned long long), st));
@@ -799,20 +686,23 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 		int err = 0;
 		unsigned long long total = 0;
 		FB_CUDA(cudaMemcpy(&err, e->d_err, sizeof err, cudaMemcpyDeviceToHost));
-		FB_CUDA(cudaMemcpy(&total, e->d_running, sizeof total, cudaMemcpyDeviceToHost));
+		FB_CUDA(cudaMemcpy(&total, e->d_running + e->run_cur, sizeof total, cudaMemcpyDeviceToHost));
 		if(total_bytes) *total_bytes = total;
+		if(err == 2) { set_error("internal: frame exceeded its size bound"); return FB200_ERR_CUDA; }
 		if(err) { set_error("output buffer too small"); return FB200_ERR_OUTPUT_TOO_SMALL; }
 	}
 	return FB200_OK;
 }
 
-int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, uint32_t first_frame_number,
-                      uint8_t *out, size_t out_capacity, uint64_t *frame_offsets, uint32_t *nframes)
+static int encode_host_impl(fb200_encoder *e, const void *pcm_any, uint32_t bytes_per_sample, uint64_t samples, uint32_t first_frame_number,
+                            uint8_t *out, size_t out_capacity, uint64_t *frame_offsets, uint32_t *nframes)
 {
 	// Host-buffer path: the batch is cut into chunks; chunk i+1's H2D copy, chunk i's kernels and
 	// chunk i-1's D2H copy run on three streams (truly asynchronous when the caller's buffers are
 	// pinned; pageable buffers still work, the copies then serialise inside the driver).
-	if(!e || (!pcm && samples) || !out || !frame_offsets) return FB200_ERR_INVALID;
+	if(!e || (!pcm_any && samples) || !out || !frame_offsets) return FB200_ERR_INVALID;
+	if(bytes_per_sample != 2 && bytes_per_sample != 3 && bytes_per_sample != 4) { set_error("bytes_per_sample must be 2, 3 or 4"); return FB200_ERR_INVALID; }
+	if(e->cfg.bits_per_sample > 8 * bytes_per_sample) { set_error("%u-bit samples do not fit %u bytes", e->cfg.bits_per_sample, bytes_per_sample); return FB200_ERR_INVALID; }
 	FB_CUDA(cudaSetDevice(e->device));
 	const uint32_t bs = e->cfg.blocksize, ch = e->cfg.channels;
 	const uint64_t nfull = samples / bs;
@@ -820,6 +710,16 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 	const uint64_t nfr = nfull + (tail ? 1 : 0);
 	if(nframes) *nframes = (uint32_t)nfr;
 	if(nfr == 0) { frame_offsets[0] = 0; return FB200_OK; }
+	const bool packed = bytes_per_sample != 4;
+	const uint8_t *pcm_bytes_host = static_cast<const uint8_t *>(pcm_any);
+	if(packed) {
+		const size_t need = (size_t)samples * ch * bytes_per_sample + 256;
+		if(need > e->d_packed_cap) {
+			cudaFree(e->d_packed); e->d_packed = nullptr; e->d_packed_cap = 0;
+			FB_CUDA(cudaMalloc(&e->d_packed, need));
+			e->d_packed_cap = need;
+		}
+	}
 	const size_t pcm_bytes = (size_t)samples * ch * sizeof(int32_t);
 	const size_t need_out = (size_t)nfr * max_frame_bytes_for(e->cfg, (int)bs) + 64;
 	if(pcm_bytes > e->d_pcm_cap) {
@@ -861,19 +761,25 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 		e->ev_h2d.push_back(ea); e->ev_comp.push_back(eb);
 	}
 	cudaStream_t sc = e->stream;
-	FB_CUDA(cudaMemsetAsync(e->d_running, 0, sizeof(unsigned long long), sc));
+	FB_CUDA(cudaMemsetAsync(e->d_running, 0, 2 * sizeof(unsigned long long), sc));
 	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), sc));
 	e->ev_b_valid[0] = e->ev_b_valid[1] = false;
 	for(size_t ci = 0; ci < used; ci++) {
 		PipeChunk &c = chunks[ci];
 		const size_t off_elems = (size_t)c.first * bs * ch;
 		const size_t nsamp = (size_t)c.nb * c.blocksize;
-		FB_CUDA(cudaMemcpyAsync(e->d_pcm + off_elems, pcm + off_elems, nsamp * ch * sizeof(int32_t), cudaMemcpyHostToDevice, e->s_h2d));
+		if(!packed) FB_CUDA(cudaMemcpyAsync(e->d_pcm + off_elems, pcm_bytes_host + off_elems * 4, nsamp * ch * sizeof(int32_t), cudaMemcpyHostToDevice, e->s_h2d));
+		else {
+			// packed 16-/24-bit PCM crosses PCIe as it is; one unpack kernel widens it to the int32 layout the pipeline reads
+			FB_CUDA(cudaMemcpyAsync(e->d_packed + off_elems * bytes_per_sample, pcm_bytes_host + off_elems * bytes_per_sample, nsamp * ch * bytes_per_sample, cudaMemcpyHostToDevice, e->s_h2d));
+			launch_unpack(e->d_packed + off_elems * bytes_per_sample, (int)bytes_per_sample, e->d_pcm + off_elems, (unsigned long long)nsamp * ch, (int)e->cfg.bits_per_sample, e->d_err, e->s_h2d);
+			e->launches++;
+		}
 		FB_CUDA(cudaEventRecord(e->ev_h2d[ci], e->s_h2d));
 		c.wait_before_a = e->ev_h2d[ci];
 		const int rc = enqueue_chunk(e, ci, c, e->d_pcm, first_frame_number, e->d_out, e->d_out_cap, e->d_offsets, sc);
 		if(rc != FB200_OK) return rc;
-		FB_CUDA(cudaMemcpyAsync(&e->h_totals[ci], e->d_running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
+		FB_CUDA(cudaMemcpyAsync(&e->h_totals[ci], e->d_running + e->run_cur, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
 		FB_CUDA(cudaEventRecord(e->ev_comp[ci], sc));
 	}
 	unsigned long long prev = 0;
@@ -889,7 +795,28 @@ int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, ui
 	FB_CUDA(cudaStreamSynchronize(sc));
 	int err = 0;
 	FB_CUDA(cudaMemcpy(&err, e->d_err, sizeof err, cudaMemcpyDeviceToHost));
+	if(err == 3) { set_error("a sample does not fit bits_per_sample"); return FB200_ERR_INVALID; }
+	if(err == 2) { set_error("internal: frame exceeded its size bound"); return FB200_ERR_CUDA; }
 	if(err) { set_error("internal output buffer too small"); return FB200_ERR_OUTPUT_TOO_SMALL; }
+	return FB200_OK;
+}
+
+int fb200_encode_host(fb200_encoder *e, const int32_t *pcm, uint64_t samples, uint32_t first_frame_number,
+                      uint8_t *out, size_t out_capacity, uint64_t *frame_offsets, uint32_t *nframes)
+{
+	return encode_host_impl(e, pcm, 4, samples, first_frame_number, out, out_capacity, frame_offsets, nframes);
+}
+
+int fb200_encode_host_packed(fb200_encoder *e, const void *pcm, uint32_t bytes_per_sample, uint64_t samples, uint32_t first_frame_number,
+                             uint8_t *out, size_t out_capacity, uint64_t *frame_offsets, uint32_t *nframes)
+{
+	return encode_host_impl(e, pcm, bytes_per_sample, samples, first_frame_number, out, out_capacity, frame_offsets, nframes);
+}
+
+int fb200_encoder_set_file_blocks(fb200_encoder *e, uint32_t blocks_per_file)
+{
+	if(!e) return FB200_ERR_INVALID;
+	e->file_blocks = blocks_per_file;
 	return FB200_OK;
 }
 
@@ -924,7 +851,7 @@ int fb200_debug_log(const double *x, double *y, uint32_t n, int device)
 	FB_CUDA(cudaMalloc(&dx, (size_t)n * sizeof(double)));
 	FB_CUDA(cudaMalloc(&dy, (size_t)n * sizeof(double)));
 	FB_CUDA(cudaMemcpy(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-	k_debug_log<<<(n + 255) / 256, 256>>>(dx, dy, (int)n);
+	launch_debug_log(dx, dy, (int)n);
 	FB_CUDA(cudaMemcpy(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
 	cudaFree(dx); cudaFree(dy);
 	return FB200_OK;

@@ -97,7 +97,93 @@ struct EncK {
 	int nsec, nwin, nslots;
 	int slot_stride;     // bytes per frame slot in the staging buffer (multiple of 16)
 	int slot_words;
-	uint32_t first_frame;
+	uint32_t first_frame;  // frame number of the call's first block
+	uint32_t blk0;         // index (inside the call) of this launch's first block
+	int file_blocks;     // > 0: frame numbers restart every file_blocks blocks (many-file batches: one stream per file, stream_encoder.c:3772)
 };
+
+// ---- k_search4 shared layout (search_kernel.cuh)
+struct SearchWarpShared4 {
+	unsigned long long leaf[kMaxPartitions];  // |residual| sums of the finest partitions of the candidate in flight
+	uint8_t params_all[2 * kMaxPartitions];   // heap: node n = (1 << po) + p
+	uint8_t b_params[kMaxPartitions];         // parameters of the best candidate so far
+};
+
+constexpr int kSearch4ZeroRow = 36;  // words of zeros in front of a warp's signal slice
+
+__host__ __device__ constexpr size_t search4_bytes_per_warp(int bs, int R_T)
+{
+	return ((size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared4) + 15) / 16 * 16;
+}
+
+
+// ---- k_emit3 (emit_kernel.cuh)
+constexpr unsigned kLbEpochMask = 0x3fffffu;  // decoupled look-back status word: value << 24 | epoch (22 bits) << 2 | flag
+// Per-launch arguments of k_emit3 beyond EncK.
+struct Emit3Args {
+	const int32_t *pcm;                  // interleaved int32, block b at pcm + b * bs * channels
+	const SigMeta *meta;                 // [nb * nsig]
+	const int *blkflags;                 // [nb]
+	const SubframePlan *plans;           // [nb * nsig]
+	const uint16_t *crc_tab;             // 4 x 256
+	uint8_t *out;
+	unsigned long long out_cap;
+	unsigned long long *offsets;         // offsets[0 .. nb] of this launch
+	const unsigned long long *running_in;  // bytes emitted by earlier launches of the same call
+	unsigned long long *running_out;
+	unsigned long long *lookback;        // [>= nb] status words
+	unsigned *ticket;                    // monotonically increasing across launches
+	unsigned ticket_base;                // value of *ticket when this launch starts
+	unsigned epoch;
+	int nb;
+	uint32_t *chan_assign_out;           // may be null
+	int *err;
+};
+
+// Fixed-size shared state of one k_emit3 CTA (in front of the signal / word buffers).
+struct Emit3Shared {
+	unsigned long long mbar;
+	unsigned long long off;      // this frame's byte offset in the output stream
+	uint32_t scan[16];           // per-warp totals of the run scan
+	uint32_t mlev[16];           // CRC combine multipliers x^(32 Lw 2^s)
+	uint32_t part[16];           // per-warp CRC partials
+	int blk, zero_words, pad0, pad1;
+	int warm[2][FB200_MAX_LPC_ORDER];  // the first 32 samples of each channel (warm-up samples / constant value)
+};
+
+__host__ __device__ inline size_t emit3_sig_bytes(int bs, int R_T, int nch)
+{
+	const size_t planar = (size_t)nch * (size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4;
+	const size_t raw = (size_t)bs * nch * 4;
+	return ((planar > raw ? planar : raw) + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t emit3_smem_bytes(int bs, int R_T, int nch, int slot_words)
+{
+	return (sizeof(Emit3Shared) + 15) / 16 * 16 + emit3_sig_bytes(bs, R_T, nch) + (size_t)(slot_words + 8) * 4;
+}
+
+
+// ---- launchers (one translation unit per kernel family; encoder.cu holds no device code)
+// general_kernels.cu
+void launch_unpack(const void *packed, int bytes_per_sample, int32_t *pcm, unsigned long long n, int bps, int *err, cudaStream_t st);
+void launch_prep(const EncK &k, const int32_t *pcm, int32_t *sig, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
+void launch_autoc_general(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
+void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, cudaStream_t st);
+void launch_search_general(const EncK &k, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st);
+void launch_emit_general(const EncK &k, size_t smem, const int32_t *sig, const int *blkflags, const SubframePlan *plans, uint8_t *slots, uint32_t *frame_bytes, uint32_t *chan_assign, int nb, cudaStream_t st);
+void launch_scan(const uint32_t *bytes, int n, unsigned long long *offsets, unsigned long long *running, cudaStream_t st);
+void launch_gather(const EncK &k, const uint8_t *slots, const uint32_t *bytes, const unsigned long long *offsets, uint8_t *out, unsigned long long capacity, int *err, int nb, cudaStream_t st);
+void launch_debug_log(const double *dx, double *dy, int n);
+void general_kernels_init(int device);  // raises the dynamic shared-memory limits once per device (never lowers them)
+// autoc_kernel.cu
+void launch_autoc3(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
+void autoc3_init(int device);
+// search_kernel.cu
+void launch_search4(const EncK &k, int rt, int maxord_t, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st);
+void search4_init(int device);
+// emit_kernel.cu
+void launch_emit3(const EncK &k, int rt, int maxord_t, size_t smem, const Emit3Args &a, int nb, cudaStream_t st);
+void launch_crc16_tables(uint16_t *tab, cudaStream_t st);
+void emit3_init(int device);
 
 }  // namespace fb200

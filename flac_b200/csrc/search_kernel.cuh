@@ -15,28 +15,9 @@
 //     the best order is tracked in registers while walking the orders downwards.
 #pragma once
 
-#include "encode_kernels_v3.cuh"
+#include "device_common.cuh"
 
 namespace fb200 {
-
-struct SearchWarpShared4 {
-	unsigned long long leaf[kMaxPartitions];  // |residual| sums of the finest partitions of the candidate in flight
-	uint8_t params_all[2 * kMaxPartitions];   // heap: node n = (1 << po) + p
-	uint8_t b_params[kMaxPartitions];         // parameters of the best candidate so far
-};
-
-constexpr int kSearch4ZeroRow = 36;  // words of zeros in front of a warp's signal slice
-
-__host__ __device__ constexpr size_t search4_bytes_per_warp(int bs, int R_T)
-{
-	return ((size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared4) + 15) / 16 * 16;
-}
-
-// int32 -> double without the conversion pipe: the bit pattern 0x43300000:(x ^ 0x80000000) is 2^52 + 2^31 + x.
-__device__ __forceinline__ double int_to_double_exact(int x)
-{
-	return __dsub_rn(__hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)), 4503601774854144.0);
-}
 
 // The 64-bit-accumulator predictor (lpc.c:786-884, subframes deeper than 16 bits) on the FP64 pipe. Measured on
 // B200 (tools/ubench): IMAD.WIDE chains run at ~13 lanes/clk/SM, DFMA at ~57. Everything here is an integer

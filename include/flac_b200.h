@@ -142,6 +142,20 @@ int fb200_encode_host(fb200_encoder *enc, const int32_t *pcm_interleaved, uint64
                       uint32_t first_frame_number, uint8_t *out, size_t out_capacity,
                       uint64_t *frame_offsets, uint32_t *nframes);
 
+/* The same for packed little-endian signed PCM, bytes_per_sample = 2 (bits_per_sample <= 16), 3 (<= 24) or 4
+ * (== fb200_encode_host): the bytes a WAV/AIFF reader holds before the reference's client widens them to int32
+ * (src/flac/encode.c:2352 format_input, feed loop :1199-1309). Half (or 3/4) of the host->device traffic of the
+ * int32 layout; one device kernel widens it. A sample outside bits_per_sample fails with FB200_ERR_INVALID
+ * (the reference's process() range check, stream_encoder.c:2543-2548). */
+int fb200_encode_host_packed(fb200_encoder *enc, const void *pcm_interleaved, uint32_t bytes_per_sample, uint64_t samples,
+                             uint32_t first_frame_number, uint8_t *out, size_t out_capacity,
+                             uint64_t *frame_offsets, uint32_t *nframes);
+
+/* Many-file batches: frame numbers restart at first_frame_number every blocks_per_file blocks, i.e. the call
+ * encodes consecutive files of blocks_per_file full blocks each, every one numbered like its own stream
+ * (stream_encoder.c:3772: frame_number = current_frame_number of that encoder). 0 = one stream (default). */
+int fb200_encoder_set_file_blocks(fb200_encoder *enc, uint32_t blocks_per_file);
+
 int fb200_encode_device(fb200_encoder *enc, const int32_t *d_pcm_interleaved, uint64_t samples,
                         uint32_t first_frame_number, uint8_t *d_out, size_t out_capacity,
                         uint64_t *d_frame_offsets, uint32_t *nframes, uint64_t *total_bytes,

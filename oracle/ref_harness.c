@@ -13,9 +13,11 @@
  * It is used by tests/ (to pin oracle/flac_oracle.c and the CUDA path against
  * the real reference) and by bench.py's reference arm / cpu_baseline.
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "FLAC/stream_encoder.h"
 #include "FLAC/stream_decoder.h"
@@ -135,6 +137,79 @@ int ref_encode(const int32_t *interleaved, uint64_t samples_per_channel,
 	if(out_len) *out_len = sink.len;
 	if(header_len) *header_len = sink.header_len;
 	if(nframes) *nframes = sink.nframes;
+	return rc;
+}
+
+/* ------------------------------------------------------------------ one encoder per host thread
+ *
+ * The "all host cores" arm for a batch of independent blocks/files: `workers` pthreads, each owning its
+ * own FLAC__StreamEncoder (num_threads = 1) and encoding a contiguous range of `blocksize`-sample blocks
+ * as its own stream ("also one process per file across all cores"). One
+ * libFLAC encoder with set_num_threads(64) serialises frame hand-off through one thread and scales
+ * far worse than this. Output bytes are discarded; *seconds = wall time from the first thread's start
+ * to the last thread's join (CLOCK_MONOTONIC). Returns 0 or the first failing worker's code. */
+typedef struct {
+	const int32_t *pcm;
+	uint64_t samples;
+	uint32_t channels, bps, sample_rate, level, blocksize;
+	const ref_enc_opts *opts;
+	size_t cap;
+	int rc;
+	size_t nframes, out_len;
+} par_job;
+
+static void *par_worker(void *arg)
+{
+	par_job *j = (par_job *)arg;
+	size_t out_len = 0, header_len = 0, nframes = 0;
+	int aux = 0;
+	j->rc = ref_encode(j->pcm, j->samples, j->channels, j->bps, j->sample_rate, j->level, j->blocksize, 1, 0, j->opts,
+	                   NULL, j->cap, &out_len, &header_len, NULL, 0, &nframes, &aux);
+	j->nframes = nframes;
+	j->out_len = out_len - header_len;
+	return NULL;
+}
+
+int ref_encode_parallel(const int32_t *interleaved, uint64_t nblocks, uint32_t channels, uint32_t bps, uint32_t sample_rate,
+                        uint32_t level, uint32_t blocksize, uint32_t workers, const ref_enc_opts *opts,
+                        double *seconds, uint64_t *frames_total, uint64_t *bytes_total)
+{
+	pthread_t *th;
+	par_job *jobs;
+	struct timespec t0, t1;
+	uint32_t w, started = 0;
+	int rc = 0;
+	uint64_t first = 0;
+	if(workers == 0 || blocksize == 0) return -1;
+	if(workers > nblocks) workers = (uint32_t)(nblocks ? nblocks : 1);
+	th = (pthread_t *)calloc(workers, sizeof *th);
+	jobs = (par_job *)calloc(workers, sizeof *jobs);
+	if(!th || !jobs) { free(th); free(jobs); return -1; }
+	for(w = 0; w < workers; w++) {
+		const uint64_t nb = nblocks / workers + (w < nblocks % workers ? 1 : 0);
+		jobs[w].pcm = interleaved + first * blocksize * channels;
+		jobs[w].samples = nb * blocksize;
+		jobs[w].channels = channels; jobs[w].bps = bps; jobs[w].sample_rate = sample_rate;
+		jobs[w].level = level; jobs[w].blocksize = blocksize; jobs[w].opts = opts;
+		jobs[w].cap = (size_t)1 << 62;
+		first += nb;
+	}
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for(w = 0; w < workers; w++) {
+		if(pthread_create(&th[w], NULL, par_worker, &jobs[w]) != 0) { rc = -1; break; }
+		started++;
+	}
+	for(w = 0; w < started; w++) pthread_join(th[w], NULL);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	if(frames_total) *frames_total = 0;
+	if(bytes_total) *bytes_total = 0;
+	for(w = 0; w < started; w++) {
+		if(jobs[w].rc != 0 && rc == 0) rc = jobs[w].rc;
+		if(frames_total) *frames_total += jobs[w].nframes;
+		if(bytes_total) *bytes_total += jobs[w].out_len;
+	}
+	if(seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+	free(th); free(jobs);
 	return rc;
 }
 

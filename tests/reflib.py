@@ -49,6 +49,11 @@ def lib(variant="default"):
         L.ref_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
                                  C.POINTER(C.c_uint32 * 4), C.c_int]
         L.ref_version.restype = C.c_char_p
+        if hasattr(L, "ref_encode_parallel"):
+            L.ref_encode_parallel.restype = C.c_int
+            L.ref_encode_parallel.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.POINTER(RefEncOpts), C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                              C.POINTER(C.c_uint64)]
         _libs[variant] = L
     return _libs[variant]
 
@@ -83,6 +88,20 @@ def encode(pcm, bps, rate=44100, level=5, blocksize=0, threads=1, md5=False, var
         pos += int(s)
     assert pos == out_len.value
     return stream.tobytes(), hdr_len.value, frames
+
+
+def encode_parallel(pcm, bps, rate, level, blocksize, workers, variant="default", opts=None):
+    """One reference encoder per host thread over contiguous block ranges (bytes discarded).
+    pcm: int32 [nblocks*blocksize, channels]. Returns (seconds, frames, frame_bytes)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    n, ch = pcm.shape
+    assert n % blocksize == 0
+    sec, nfr, nby = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+    rc = lib(variant).ref_encode_parallel(pcm.ctypes.data, n // blocksize, ch, bps, rate, level, blocksize, workers,
+                                          C.byref(opts) if opts is not None else None, C.byref(sec), C.byref(nfr), C.byref(nby))
+    if rc != 0:
+        raise RuntimeError(f"ref_encode_parallel failed rc={rc}")
+    return sec.value, nfr.value, nby.value
 
 
 def decode(stream, max_samples, channels, variant="default", md5=False):

@@ -101,10 +101,10 @@ def test_setters_and_validation_without_device(lib):
 
 
 def test_crc16_power_table_constants():
-    """kCrcXPow2 in encode_kernels.cuh (x^(2^j) mod x^16+x^15+x^2+1, used to combine chunk CRCs) recomputed from
+    """kCrcXPow2 in device_common.cuh (x^(2^j) mod x^16+x^15+x^2+1, used to combine chunk CRCs) recomputed from
     scratch, and the combine identity crc(A||B) = crc(A) * x^(8|B|) + crc(B) checked against a bytewise CRC-16."""
     import re
-    src = open(os.path.join(os.path.dirname(__file__), "..", "flac_b200", "csrc", "encode_kernels.cuh")).read()
+    src = open(os.path.join(os.path.dirname(__file__), "..", "flac_b200", "csrc", "device_common.cuh")).read()
     m = re.search(r"kCrcXPow2\[15\]\s*=\s*\{([^}]*)\}", src)
     table = [int(v, 16) for v in m.group(1).replace(" ", "").split(",")]
 

@@ -160,25 +160,76 @@ def test_big_batch_property_round_trip():
     enc.close()
 
 
-@pytest.mark.parametrize("env", [{"FB200_FORCE_GENERAL_KERNELS": "1"}, {"FB200_SEARCH_KERNEL": "3"}, {"FB200_SEARCH_KERNEL": "2"}, {"FB200_SEARCH_KERNEL": "1"},
-                                 {"FB200_AUTOC_SPLIT": "1"}, {"FB200_AUTOC_KERNEL": "2"}])
-@pytest.mark.parametrize("level,ch,bps", [(8, 2, 16), (5, 2, 16), (8, 2, 24), (2, 1, 16)])
-def test_every_kernel_generation_is_bit_exact(env, level, ch, bps, monkeypatch):
-    """The general kernels (any blocksize), the v2 CTA-per-signal search and the split autocorrelation are
-    selectable at encoder creation; each must reproduce the oracle's frames on standard blocksizes too."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+@pytest.mark.parametrize("level,ch,bps", [(8, 2, 16), (5, 2, 24), (5, 1, 16), (2, 2, 16), (8, 2, 24)])
+def test_general_kernels_equal_fast_kernels(monkeypatch, level, ch, bps):
+    """FB200_FORCE_GENERAL_KERNELS=1 runs the general kernels (any blocksize) on a blocksize the fast kernels
+    (k_autoc3 / k_search4 / k_emit3) normally take: both must give the oracle's frames."""
+    monkeypatch.setenv("FB200_FORCE_GENERAL_KERNELS", "1")
     x = signals.music_like(4096 * 3 + 55, ch, bps, 44100, seed=17)
     got = _gpu_frames(x, bps, 44100, level)
-    _assert_same(got, _oracle_frames(x, bps, 44100, level), f"{env}")
+    _assert_same(got, _oracle_frames(x, bps, 44100, level), "general kernels")
 
 
-@pytest.mark.xfail(strict=False, reason="k_search4's 32-tap instantiation mis-evaluated orders > 16 when first written; "
-                                        "the default path keeps k_search3 for max_lpc_order > 12 until this passes reliably")
-def test_search4_32tap_experimental(monkeypatch):
-    """FB200_SEARCH_KERNEL=5 forces k_search4 for max_lpc_order > 12 as well (not the default dispatch)."""
-    monkeypatch.setenv("FB200_SEARCH_KERNEL", "5")
-    for bps, mlo in ((16, 32), (12, 20), (24, 32)):
-        x = signals.music_like(4096 * 2 + 99, 2, bps, 44100, seed=2)
-        got = _gpu_frames(x, bps, 44100, 8, max_lpc_order=mlo)
-        _assert_same(got, _oracle_frames(x, bps, 44100, 8, max_lpc_order=mlo), f"bps {bps} max_lpc_order {mlo}")
+@pytest.mark.parametrize("bps", [16, 12, 24, 20])
+@pytest.mark.parametrize("mlo", [13, 16, 17, 20, 24, 32])
+def test_search4_orders_13_to_32(bps, mlo):
+    """k_search4's 32-tap instantiation (max_lpc_order 13..32) is the default for every regular blocksize.
+    Round 1 kept orders > 12 on the previous kernel generation because a first version of k_search4 mis-evaluated
+    orders > 16; that version handled the warm-up samples with a masked first tile (group-relative order mask for
+    MAXORD > G), which commit ef78d8c replaced by one unmasked pass + a warm-up correction. This matrix
+    (tools/probe_search4_32.py is the longer form: 108 configurations, 0 of 432 frames differ) pins it."""
+    for bs, ex in ((4096, 0), (4608, 0), (1024, 0), (2304, 0), (4096, 1)):
+        if ex and mlo > 17:
+            continue
+        over = dict(max_lpc_order=mlo)
+        if ex:
+            over["do_exhaustive_model_search"] = 1
+        x = signals.music_like(bs * 2 + 99, 2, bps, 44100, seed=2 + mlo % 5)
+        got = _gpu_frames(x, bps, 44100, 8, bs, **over)
+        _assert_same(got, _oracle_frames(x, bps, 44100, 8, bs, **over), f"bps {bps} max_lpc_order {mlo} bs {bs} exhaustive {ex}")
+
+
+@pytest.mark.parametrize("bps,nbytes,ch", [(16, 2, 2), (12, 2, 2), (24, 3, 2), (20, 3, 1), (16, 3, 2), (16, 2, 1)])
+def test_packed_pcm_entry_point(bps, nbytes, ch):
+    """fb200_encode_host_packed (16-/24-bit little-endian PCM, widened on the device) == the int32 entry point == oracle."""
+    import flac_b200
+    n = 4096 * 5 + 1234 + (1 if nbytes == 3 else 0)  # odd byte offsets for the short last block too
+    x = signals.music_like(n, ch, bps, 44100, seed=21)
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, 44100, 5), max_blocks_per_launch=2)
+    try:
+        stream, offs = enc.encode_packed(flac_b200.pack_pcm(x, nbytes), nbytes, n)
+        got = [stream[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(offs) - 1)]
+    finally:
+        enc.close()
+    _assert_same(got, _oracle_frames(x, bps, 44100, 5), f"packed {nbytes} bytes/sample")
+
+
+def test_packed_pcm_out_of_range_sample_fails():
+    import flac_b200
+    x = signals.music_like(4096 * 2, 2, 16, 44100, seed=3)  # 16-bit samples into a 12-bit stream
+    enc = flac_b200.Encoder(flac_b200.preset(2, 12, 44100, 5))
+    try:
+        with pytest.raises(flac_b200.FlacB200Error) as ei:
+            enc.encode_packed(flac_b200.pack_pcm(x, 2), 2, x.shape[0])
+        assert ei.value.code == -3
+    finally:
+        enc.close()
+
+
+@pytest.mark.parametrize("ch,bps,level", [(2, 16, 5), (8, 24, 8), (1, 16, 8)])
+def test_file_blocks_restarts_frame_numbers(ch, bps, level):
+    """Many-file batches: with set_file_blocks(n) every run of n blocks is numbered like its own stream
+    (reference: one encoder per file, frame_number from 0, stream_encoder.c:3772)."""
+    import flac_b200
+    per_file, files = 6, 3
+    x = signals.music_like(4096 * per_file * files, ch, bps, 44100, seed=5)
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, 44100, level), max_blocks_per_launch=7)
+    try:
+        enc.set_file_blocks(per_file)
+        got = enc.encode_frames(x)
+    finally:
+        enc.close()
+    want = []
+    for f in range(files):
+        want += _oracle_frames(x[f * per_file * 4096:(f + 1) * per_file * 4096], bps, 44100, level)
+    _assert_same(got, want, "file-major frame numbering")
