@@ -276,7 +276,7 @@ class Decoder:
     def launches(self):
         return int(lib().fb200_decoder_launch_count(self._h))
 
-    PROF_NAMES = ("k_dec_parse", "k_dec_crc", "k_dec_merge")
+    PROF_NAMES = ("k_dec_walk", "k_dec_crc", "k_dec_frames")
 
     def set_profiling(self, on=True):
         _check(lib().fb200_decoder_set_profiling(self._h, 1 if on else 0))

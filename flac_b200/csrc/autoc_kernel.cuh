@@ -143,4 +143,142 @@ __global__ void __launch_bounds__(32) k_autoc3(EncK P, const int32_t *__restrict
 	}
 }
 
+
+// ================================================================ k_autoc4
+// The same chain-per-thread scheme fed from the CALLER'S interleaved int32 PCM (no planar copy): the warp's 32 chains
+// are 32 consecutive (block, signal) items of one section, i.e. a handful of blocks; per tile the raw rows of those
+// blocks (T samples x channels) and the section's weight tile are staged with 1-D TMA bulk copies onto an mbarrier
+// ring (cp.async.bulk + mbarrier::complete_tx: one copy per block row instead of T/4 16-byte cp.async per lane), and
+// every lane derives ITS signal from the raw row on the fly: channel c, or mid = (L+R)>>1 / side = L-R
+// (stream_encoder.c:3823-3836), wasted bits shifted out (:3842-3867). The per-section weight table (host-built,
+// zero outside the section) turns the partial windows of lpc.c:82-94 into plain weights.
+// MODE 0: mono (128-bit row reads = 4 samples); 1: two channels (128-bit = 2 sample pairs, signal = (a L + b R) >> sh);
+// 2: any channel count (scalar reads).
+__host__ __device__ constexpr int autoc4_rows_max(int nsig) { return (nsig + 30) / nsig + 1; }
+__host__ __device__ constexpr int autoc4_row_stride(int T, int ch, int mode)
+{
+	// words; multiples of 4 (TMA destination alignment); modes 0/1: an odd number of 16-byte units -> the 128-bit reads
+	// of distinct rows fall into distinct bank groups; mode 2: rows 8 banks apart
+	return mode == 2 ? T * ch + 8 : (((T * ch / 4) & 1) ? T * ch : T * ch + 4);
+}
+template <int U, int K, int STAGES>
+__host__ __device__ constexpr size_t autoc4_smem_bytes(int nsig, int ch, int mode)
+{
+	return 64 + (size_t)STAGES * ((size_t)autoc4_rows_max(nsig) * autoc4_row_stride(U * K, ch, mode) + U * K) * 4;
+}
+
+template <int LAGS, int U, int K, int STAGES, int MODE>
+__global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict__ pcm, const SigMeta *__restrict__ meta,
+                                              const float *__restrict__ secwin, int secwin_stride, const DevSection *__restrict__ secs,
+                                              double *__restrict__ autoc, int nitems)
+{
+	static_assert(U % LAGS == 0 && U % 4 == 0, "a body must be a whole number of history rotations and of 128-bit loads");
+	constexpr int T = U * K;
+	extern __shared__ int4 autoc4_smem[];
+	uint64_t *const bars = reinterpret_cast<uint64_t *>(autoc4_smem);  // STAGES mbarriers in the first 64 bytes
+	int *const smem = reinterpret_cast<int *>(autoc4_smem) + 16;
+	const int lane = threadIdx.x, nsig = P.nsig, ch = P.channels, bs = P.bs;
+	const int RS = autoc4_row_stride(T, ch, MODE);
+	const int STAGE_WORDS = autoc4_rows_max(nsig) * RS + T;
+
+	// section slowest: the longest chains (full-length sections) start first (see k_autoc3)
+	const int groups = (nitems + 31) >> 5;
+	const int sec = blockIdx.x / groups;
+	const int item0 = (blockIdx.x - sec * groups) << 5;
+	const int item = min(item0 + lane, nitems - 1);
+	const SigMeta M = meta[item];
+	const bool live = item0 + lane < nitems && M.bps != 0;
+	if(!__any_sync(0xffffffffu, live)) return;
+
+	const DevSection S = secs[sec];
+	const int shift = S.partial ? S.data_shift : 0;
+	const int a0 = shift & ~3;                                    // 16-byte aligned first sample fetched
+	const int nvalid = S.partial ? 2 * S.part_size : S.data_len;  // weights are 0 from here on (lpc.c:90-91): nothing to add
+	const int ntiles = (shift - a0 + nvalid + T - 1) / T;
+	const int b0 = item0 / nsig;
+	const int nrows = min(item0 + 31, nitems - 1) / nsig - b0 + 1;
+	const int myrow = item / nsig - b0, sidx = item - (item / nsig) * nsig;
+	const float *wsec = secwin + (size_t)sec * secwin_stride;
+
+	// this lane's signal as (a * X + b * Y) >> sh of the raw row; X = channel c0, Y = channel 1 (two-channel mode only)
+	int ca = 1, cb = 0, sh = M.wasted;
+	if(MODE == 1) {
+		if(sidx == 1) { ca = 0; cb = 1; }
+		else if(sidx == 2) { ca = 1; cb = 1; sh += 1; }
+		else if(sidx == 3) { ca = 1; cb = -1; }
+	}
+
+	if(lane == 0) {
+#pragma unroll
+		for(int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+		mbar_fence_init();
+	}
+	__syncwarp();
+
+	auto issue = [&](int t) {
+		if(t < ntiles) {
+			const int stg = t % STAGES;
+			int *st = smem + stg * STAGE_WORDS;
+			const int start = a0 + t * T;
+			const int n = min(T, bs - start);  // never read past the block (the last block ends the caller's buffer)
+			const unsigned row_bytes = (unsigned)n * (unsigned)ch * 4u;
+			if(lane == 0) mbar_expect_tx(&bars[stg], (unsigned)nrows * row_bytes + (unsigned)T * 4u);
+			__syncwarp();
+			if(lane < nrows) tma_bulk_g2s(st + lane * RS, pcm + ((size_t)(b0 + lane) * bs + start) * ch, row_bytes, &bars[stg]);
+			if(lane == (nrows < 32 ? nrows : 0)) tma_bulk_g2s(st + autoc4_rows_max(nsig) * RS, wsec + start, (unsigned)T * 4u, &bars[stg]);  // the table has T zeros of slack
+		}
+	};
+
+	double acc[LAGS], h[LAGS];
+#pragma unroll
+	for(int l = 0; l < LAGS; l++) { acc[l] = 0.0; h[l] = 0.0; }
+
+#pragma unroll
+	for(int t = 0; t < STAGES - 1; t++) issue(t);
+	for(int t = 0; t < ntiles; t++) {
+		__syncwarp();                 // every lane is done with tile t-1's buffer ...
+		issue(t + STAGES - 1);        // ... which is the one refilled now
+		mbar_wait(&bars[t % STAGES], (unsigned)(t / STAGES) & 1u);
+		const int *row = smem + (t % STAGES) * STAGE_WORDS + myrow * RS;
+		const float *win = reinterpret_cast<const float *>(smem + (t % STAGES) * STAGE_WORDS + autoc4_rows_max(nsig) * RS);
+#pragma unroll 1
+		for(int kb = 0; kb < K; kb++) {
+#pragma unroll
+			for(int q = 0; q < U / 4; q++) {
+				int xs4[4];
+				if(MODE == 0) {
+					const int4 xq = *reinterpret_cast<const int4 *>(row + kb * U + q * 4);
+					xs4[0] = xq.x >> sh; xs4[1] = xq.y >> sh; xs4[2] = xq.z >> sh; xs4[3] = xq.w >> sh;
+				}
+				else if(MODE == 1) {
+					const int4 p0 = *reinterpret_cast<const int4 *>(row + 2 * (kb * U + q * 4));
+					const int4 p1 = *reinterpret_cast<const int4 *>(row + 2 * (kb * U + q * 4) + 4);
+					xs4[0] = (ca * p0.x + cb * p0.y) >> sh; xs4[1] = (ca * p0.z + cb * p0.w) >> sh;
+					xs4[2] = (ca * p1.x + cb * p1.y) >> sh; xs4[3] = (ca * p1.z + cb * p1.w) >> sh;
+				}
+				else {
+#pragma unroll
+					for(int e = 0; e < 4; e++) xs4[e] = row[(kb * U + q * 4 + e) * ch + sidx] >> sh;
+				}
+				const float4 wq = *reinterpret_cast<const float4 *>(win + kb * U + q * 4);
+				const float ws[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+				for(int e = 0; e < 4; e++) {
+					const int u = q * 4 + e;
+					const double dv = (double)__fmul_rn((float)xs4[e], ws[e]);  // lpc.c:68-74: float product, widened
+					const int su = (LAGS - (u % LAGS)) % LAGS;                   // slot of the newest sample; slot (su+l)%LAGS holds d[i-l]
+					h[su] = dv;
+#pragma unroll
+					for(int l = 0; l < LAGS; l++) acc[l] = fma(dv, h[(su + l) % LAGS], acc[l]);
+				}
+			}
+		}
+	}
+	if(live) {
+		double *out = autoc + ((size_t)sec * nitems + item) * P.lag_stride;
+#pragma unroll
+		for(int l = 0; l < LAGS; l++) out[l] = acc[l];
+	}
+}
+
 }  // namespace fb200

@@ -1,14 +1,22 @@
 // decode_kernels.cuh -- sm_100a kernels of the FLAC batch frame decoder.
 //
-// Frames carry no length field and Rice codes have data-dependent lengths, so parsing a frame is
-// a serial recurrence; parallelism is across frames:
-//   k_dec_parse : one THREAD per frame -- header, subframes, Rice decode fused with the
-//                 fixed/LPC restore (history in registers), planar int32 scratch output
-//                 (stream_decoder.c:2373-3357, lpc.c:978-1491, fixed.c:571-629)
-//   k_dec_crc   : one WARP per frame -- CRC-16 of the frame bytes, chunked + GF(2) combine
-//                 (stream_decoder.c:2443-2452, crc.c:78-396)
-//   k_dec_merge : undo channel decorrelation + interleave, fully coalesced
-//                 (stream_decoder.c:3476-3527)
+// Frames carry no length field and Rice codes have data-dependent lengths: where subframe c+1 starts is only known
+// once subframe c has been walked, and the LPC restore is a serial recurrence. Round 1 ran the whole
+// frame in one thread (header, every subframe, Rice decode fused with the restore, planar scratch, then a merge pass):
+// 89 % of the decode step at 2.6 % of HBM, divergent (32 different frames per warp, each in a different loop nest) and
+// with 4-byte stores 16 KB apart. This generation splits the frame along its only parallel axis, the channels:
+//   k_dec_walk   : one thread per frame -- header (stream_decoder.c:2624-2947) + CRC-8, then a WALK over subframes
+//                  0..channels-2 that only measures them (unary length + k per code, no sample is formed): the bit
+//                  offset of every subframe. ~10 instructions per code.
+//   k_dec_frames : one LANE per (frame, channel), the lanes of a frame adjacent in a warp and in lock step over the
+//                  sample index: Rice decode (deduplication/bitreader_read_rice_signed_block.c) fused with the
+//                  fixed/LPC restore (lpc.c:978-1491, fixed.c:571-629) with the history in registers, inter-channel
+//                  decorrelation undone through a shuffle (stream_decoder.c:3476-3527), interleaved PCM written
+//                  directly (the lanes of a frame store adjacent words). No scratch, no merge pass. All per-sample
+//                  decisions (partition change, escape, verbatim, constant) are data, not control flow, so the 32 lanes
+//                  of a warp stay converged although they decode different subframes.
+//   k_dec_crc    : one warp per frame -- CRC-16 of the frame bytes (crc.c:78-396), slicing-by-4 + GF(2) combine.
+// Reads never leave the frame: the bit reader returns zeros past the frame's last word (untrusted input).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -20,12 +28,12 @@ namespace fb200 {
 
 enum : uint32_t {
 	DEC_OK = 0, DEC_BAD_SYNC = 1, DEC_BAD_HEADER = 2, DEC_CRC8 = 3, DEC_UNSUPPORTED = 4, DEC_PARSE = 5,
-	DEC_LENGTH = 6, DEC_CRC16 = 7, DEC_MISMATCH = 8
+	DEC_LENGTH = 6, DEC_CRC16 = 7, DEC_MISMATCH = 8, DEC_RANGE = 9
 };
 
 struct DecK {
 	int channels, bps, sample_rate, blocksize;  // STREAMINFO facts
-	int bs_stride;                              // planar scratch stride per channel
+	int loose_end;                               // 1: a frame's given end is an upper bound (index mode); 0: it must be exact
 };
 
 struct DecFrameMeta {
@@ -33,129 +41,111 @@ struct DecFrameMeta {
 	uint32_t blocksize;
 	uint32_t channel_assignment;  // 0 independent, 1 left/side, 2 right/side, 3 mid/side
 	uint32_t channels;
+	uint32_t sub_bit[FB200_MAX_CHANNELS];  // bit offset (from the frame's first byte) of every subframe
+	uint32_t frame_bytes;         // parsed length including the CRC-16 (k_dec_frames)
+	uint32_t frame_number_lo;     // low 32 bits of the coded frame / sample number
+	uint32_t variable;            // 1: variable blocksize stream (the number is a sample number)
+	uint32_t sample_rate;
+	uint32_t max_order;           // largest predictor order among the frame's subframes (selects the k_dec_frames instantiation)
 };
 
-// MSB-first bit reader over global memory with a two-word register cache.
-struct BitReader {
-	const uint32_t *words;  // aligned base
-	uint32_t pos;           // bit position relative to words[0]
-	uint32_t end;           // one past the last valid bit
-	uint32_t w0, w1;        // big-endian words at index (pos>>5), +1
-	uint32_t widx;
-	__device__ __forceinline__ static uint32_t be(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
-	__device__ __forceinline__ void init(const uint8_t *p, uint32_t nbytes)
+// What a client sees of one subframe (FLAC__Subframe, include/FLAC/format.h:211-484) -- filled on request.
+struct DecSubframeInfo {
+	uint8_t type;       // 0 constant, 1 verbatim, 2 fixed, 3 lpc
+	uint8_t order;
+	uint8_t wasted;
+	uint8_t precision;  // lpc
+	int8_t shift;       // lpc
+	uint8_t method;     // 0 RICE, 1 RICE2
+	uint8_t porder;
+	uint8_t pad;
+	int32_t qlp[FB200_MAX_LPC_ORDER];
+	int32_t warmup[FB200_MAX_LPC_ORDER];  // warm-up samples (constant: [0] = the value)
+};
+
+// MSB-first bit reader over global memory: 64-bit left-aligned accumulator, at least 32 valid bits after every refill,
+// zeros past word `nwords`.
+struct BitRd {
+	const uint32_t *words;
+	uint32_t nwords, widx, pos, end;
+	unsigned long long acc;
+	int nbits;
+	__device__ __forceinline__ uint32_t load(uint32_t i) const { return i < nwords ? __byte_perm(__ldg(words + i), 0, 0x0123) : 0u; }
+	// p: first byte of the frame, len: frame bytes, bit: bit offset inside the frame to start at
+	__device__ __forceinline__ void init(const uint8_t *p, uint32_t len, uint32_t bit)
 	{
 		const uintptr_t a = reinterpret_cast<uintptr_t>(p);
 		words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-		pos = (uint32_t)(a & 3) * 8;
-		end = pos + nbytes * 8;
-		widx = 0;
-		w0 = be(__ldg(words));
-		w1 = be(__ldg(words + 1));
+		const uint32_t lead = (uint32_t)(a & 3) * 8;
+		nwords = (lead + len * 8 + 31) >> 5;
+		end = lead + len * 8;
+		pos = lead + bit;
+		reseat();
 	}
-	__device__ __forceinline__ void sync_words()
+	__device__ __forceinline__ void refill()
 	{
-		const uint32_t wi = pos >> 5;
-		if(wi != widx) {
-			if(wi == widx + 1) { w0 = w1; w1 = be(__ldg(words + wi + 1)); }
-			else { w0 = be(__ldg(words + wi)); w1 = be(__ldg(words + wi + 1)); }
-			widx = wi;
+		if(nbits <= 32) {
+			acc |= (unsigned long long)load(widx++) << (32 - nbits);
+			nbits += 32;
 		}
 	}
-	__device__ __forceinline__ uint32_t peek32()  // next 32 bits (zero-extended past `end` is the caller's problem)
+	__device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(acc >> 32); }
+	__device__ __forceinline__ void consume(uint32_t n)  // 0..32
 	{
-		sync_words();
-		return __funnelshift_l(w1, w0, pos & 31);
+		acc <<= n;
+		nbits -= (int)n;
+		pos += n;
+		refill();
 	}
-	__device__ __forceinline__ uint32_t get(uint32_t n)  // 1..32 bits
+	__device__ __forceinline__ uint32_t get(uint32_t n)  // 1..32
 	{
 		const uint32_t v = peek32() >> (32 - n);
-		pos += n;
+		consume(n);
 		return v;
 	}
-	__device__ __forceinline__ int32_t get_signed(uint32_t n)
+	__device__ __forceinline__ int32_t get_signed(uint32_t n)  // 1..32
 	{
 		const int32_t v = (int32_t)peek32() >> (32 - n);
-		pos += n;
+		consume(n);
 		return v;
 	}
-	__device__ __forceinline__ uint32_t unary()  // number of 0 bits before the next 1 (bitreader.c:725)
+	__device__ __forceinline__ void reseat()  // after pos was moved arbitrarily
+	{
+		widx = pos >> 5;
+		acc = ((unsigned long long)load(widx) << 32) | load(widx + 1);
+		widx += 2;
+		nbits = 64;
+		const uint32_t r = pos & 31u;
+		acc <<= r;
+		nbits -= (int)r;
+		refill();
+	}
+	__device__ __forceinline__ void skip(uint32_t n)  // any number of bits
+	{
+		if(n <= 32u) consume(n);
+		else {
+			pos = (n > 0x7fffffffu - pos) ? 0x7fffffffu : pos + n;  // saturate: corrupt streams must not wrap the position
+			reseat();
+		}
+	}
+	// number of 0 bits before the next 1, consumed together with the 1 (bitreader.c:725)
+	__device__ __forceinline__ uint32_t unary()
 	{
 		uint32_t q = 0;
-		while(true) {
-			const uint32_t v = peek32();
-			if(v) {
-				const uint32_t z = (uint32_t)__clz((int)v);
-				pos += z + 1;
-				return q + z;
-			}
-			q += 32;
-			pos += 32;
+		uint32_t v = peek32();
+		while(v == 0) {
 			if(pos > end) return q;
+			q += 32;
+			consume(32);
+			v = peek32();
 		}
+		const uint32_t z = (uint32_t)__clz((int)v);
+		consume(z + 1);
+		return q + z;
 	}
 	__device__ __forceinline__ bool overrun() const { return pos > end; }
 };
 
-// Restores MAXORD-tap predicted samples on the fly: hist[j] = sample (i-1-j).
-template <int MAXORD, bool WIDE>
-__device__ __forceinline__ int32_t predict(const int (&q)[MAXORD], const int (&hist)[MAXORD], int shift)
-{
-	if(WIDE) {
-		long long sum = 0;
-#pragma unroll
-		for(int j = 0; j < MAXORD; j++) sum += (long long)q[j] * (long long)hist[j];
-		return (int32_t)(sum >> shift);
-	}
-	else {
-		int sum = 0;
-#pragma unroll
-		for(int j = 0; j < MAXORD; j++) sum += q[j] * hist[j];
-		return sum >> shift;
-	}
-}
-
-// Decode the residual of one subframe and restore the signal in the same pass.
-// q[] = predictor taps (zero beyond the order), warm-up already in hist[] and written to out.
-template <int MAXORD, bool WIDE>
-__device__ bool decode_residual_restore(BitReader &br, uint32_t blocksize, uint32_t order, const int (&q)[MAXORD], int shift,
-                                        int (&hist)[MAXORD], int32_t *__restrict__ out, uint32_t wasted)
-{
-	// stream_decoder.c:3299-3357 read_residual_partitioned_rice_
-	const uint32_t method = br.get(2);
-	if(method > 1) return false;
-	const uint32_t plen = method ? kRice2ParamLen : kRiceParamLen, pesc = method ? kRice2Escape : kRiceEscape;
-	const uint32_t po = br.get(4);
-	const uint32_t psamples = blocksize >> po;
-	if(po > 0 ? (psamples < order || (psamples << po) != blocksize) : blocksize < order) return false;
-	uint32_t i = order;
-	for(uint32_t p = 0; p < (1u << po); p++) {
-		const uint32_t k = br.get(plen);
-		const uint32_t pend = (po == 0) ? blocksize : (p + 1) * psamples;
-		uint32_t raw = 0;
-		const bool esc = k >= pesc;
-		if(esc) raw = br.get(5);
-		for(; i < pend; i++) {
-			int32_t r;
-			if(!esc) {
-				// deduplication/bitreader_read_rice_signed_block.c: unary MSBs, k LSBs, zig-zag
-				const uint32_t msbs = br.unary();
-				const uint32_t u = (msbs << k) | (k ? br.get(k) : 0u);
-				r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-			}
-			else r = raw ? br.get_signed(raw) : 0;
-			const int32_t v = r + predict<MAXORD, WIDE>(q, hist, shift);
-#pragma unroll
-			for(int j = MAXORD - 1; j > 0; j--) hist[j] = hist[j - 1];
-			hist[0] = v;
-			out[i] = (int32_t)((uint32_t)v << wasted);
-		}
-		if(br.overrun()) return false;
-	}
-	return true;
-}
-
-__device__ __forceinline__ uint32_t dec_ilog2(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
 __device__ __forceinline__ uint32_t dec_silog2(long long v)
 {
 	if(v == 0) return 0;
@@ -164,89 +154,49 @@ __device__ __forceinline__ uint32_t dec_silog2(long long v)
 	return (63u - (uint32_t)__clzll(v)) + 2;
 }
 
-template <int MAXORD>
-__device__ bool decode_predicted(BitReader &br, uint32_t blocksize, uint32_t order, const int *qsrc, int shift, bool wide,
-                                 uint32_t bps, int32_t *__restrict__ out, uint32_t wasted)
-{
-	int q[MAXORD], hist[MAXORD];
-#pragma unroll
-	for(int j = 0; j < MAXORD; j++) { q[j] = (j < (int)order) ? qsrc[j] : 0; hist[j] = 0; }
-	// warm-up samples were already read into out[0..order) (unshifted) by the caller
-#pragma unroll
-	for(int j = 0; j < MAXORD; j++)
-		if(j < (int)order) hist[j] = out[order - 1 - j];
-	for(uint32_t i = 0; i < order; i++) out[i] = (int32_t)((uint32_t)out[i] << wasted);
-	(void)bps;
-	if(wide) return decode_residual_restore<MAXORD, true>(br, blocksize, order, q, shift, hist, out, wasted);
-	return decode_residual_restore<MAXORD, false>(br, blocksize, order, q, shift, hist, out, wasted);
-}
+// ---------------------------------------------------------------- subframe header (stream_decoder.c:2949-3297)
+struct SubHdr {
+	uint32_t type;     // 0 constant, 1 verbatim, 2 fixed, 3 lpc, 255 invalid
+	uint32_t order, wasted, bps;  // bps: after wasted bits
+	uint32_t precision;
+	int shift;
+};
 
-// stream_decoder.c:2949-3297 read_subframe_*
-__device__ bool decode_subframe(BitReader &br, uint32_t blocksize, uint32_t bps, int32_t *__restrict__ out)
+// reads the 8-bit subframe header (+ unary wasted bits); the reader is left at the first warm-up / constant / verbatim bit
+__device__ __forceinline__ SubHdr read_sub_header(BitRd &br, uint32_t bps)
 {
+	SubHdr h;
+	h.type = 255; h.order = 0; h.wasted = 0; h.bps = bps; h.precision = 0; h.shift = 0;
 	uint32_t x = br.get(8);
-	if(x & 0x80) return false;
-	uint32_t wasted = 0;
+	if(x & 0x80) return h;
 	if(x & 1) {
-		wasted = br.unary() + 1;
-		if(wasted >= bps) return false;
-		bps -= wasted;
+		h.wasted = br.unary() + 1;
+		if(h.wasted >= bps) return h;
+		h.bps = bps - h.wasted;
 	}
 	x &= 0xfe;
-	if(x == 0) {  // CONSTANT
-		const int32_t v = (int32_t)((uint32_t)br.get_signed(bps) << wasted);
-		for(uint32_t i = 0; i < blocksize; i++) out[i] = v;
-		return !br.overrun();
-	}
-	if(x == 2) {  // VERBATIM
-		for(uint32_t i = 0; i < blocksize; i++) out[i] = (int32_t)((uint32_t)br.get_signed(bps) << wasted);
-		return !br.overrun();
-	}
-	if(x >= 16 && x <= 24) {  // FIXED (fixed.c:571-629 as taps)
-		const uint32_t order = (x >> 1) & 7;
-		if(order > 4 || blocksize <= order) return false;
-		for(uint32_t i = 0; i < order; i++) out[i] = br.get_signed(bps);
-		const int tab[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-		// 32-bit restore when bps + order <= 32 (stream_decoder.c:3139-3143); int64 otherwise. With bps <= 25
-		// both agree with wrapping int32 arithmetic on the sums the reference forms.
-		return decode_predicted<4>(br, blocksize, order, tab[order], 0, false, bps, out, wasted);
-	}
-	if(x >= 64) {  // LPC
-		const uint32_t order = ((x >> 1) & 31) + 1;
-		if(blocksize <= order) return false;
-		for(uint32_t i = 0; i < order; i++) out[i] = br.get_signed(bps);
-		const uint32_t prec = br.get(4);
-		if(prec == 15) return false;
-		const uint32_t precision = prec + 1;
-		const int shift = br.get_signed(5);
-		if(shift < 0) return false;
-		int q[FB200_MAX_LPC_ORDER];
-		uint32_t abs_sum = 0;
-		for(uint32_t j = 0; j < order; j++) { q[j] = br.get_signed(precision); abs_sum += (uint32_t)abs(q[j]); }
-		// variant rule of stream_decoder.c:3243-3247 (lpc.c:942-968)
-		const unsigned long long max_abs = 1ull << (bps - 1);
-		const unsigned long long max_pred = max_abs * abs_sum;
-		const unsigned long long max_after = (unsigned long long)(-1 * ((-1 * (long long)max_pred) >> shift));
-		const bool wide = !(dec_silog2((long long)(max_abs + max_after)) <= 32 && dec_silog2((long long)max_pred) <= 32);
-		if(order <= 8) return decode_predicted<8>(br, blocksize, order, q, shift, wide, bps, out, wasted);
-		if(order <= 12) return decode_predicted<12>(br, blocksize, order, q, shift, wide, bps, out, wasted);
-		return decode_predicted<32>(br, blocksize, order, q, shift, wide, bps, out, wasted);
-	}
-	return false;  // reserved subframe type
+	if(x == 0) h.type = 0;
+	else if(x == 2) h.type = 1;
+	else if(x >= 16 && x <= 24) { h.type = 2; h.order = (x >> 1) & 7; if(h.order > 4) h.type = 255; }
+	else if(x >= 64) { h.type = 3; h.order = ((x >> 1) & 31) + 1; }
+	return h;
 }
 
-__global__ void __launch_bounds__(64) k_dec_parse(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets,
-                                                 int nframes, int32_t *__restrict__ scratch, DecFrameMeta *__restrict__ meta)
+// ================================================================ k_dec_walk
+__global__ void __launch_bounds__(128) k_dec_walk(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets,
+                                                 int nframes, DecFrameMeta *__restrict__ meta)
 {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if(f >= nframes) return;
 	const unsigned long long off = offsets[f];
 	const uint32_t len = (uint32_t)(offsets[f + 1] - off);
 	DecFrameMeta M;
-	M.status = DEC_OK; M.blocksize = 0; M.channel_assignment = 0; M.channels = 0;
+	M.status = DEC_OK; M.blocksize = 0; M.channel_assignment = 0; M.channels = 0; M.frame_bytes = 0; M.frame_number_lo = 0; M.variable = 0; M.sample_rate = 0; M.max_order = 0;
+#pragma unroll
+	for(int c = 0; c < FB200_MAX_CHANNELS; c++) M.sub_bit[c] = 0;
 	if(len < 6) { M.status = DEC_LENGTH; meta[f] = M; return; }
-	BitReader br;
-	br.init(frames + off, len);
+	BitRd br;
+	br.init(frames + off, len, 0);
 	const uint32_t start = br.pos;
 
 	// ---- frame header (stream_decoder.c:2624-2947)
@@ -255,19 +205,23 @@ __global__ void __launch_bounds__(64) k_dec_parse(DecK P, const uint8_t *__restr
 	const uint32_t variable = br.get(1);
 	const uint32_t bs_code = br.get(4), sr_code = br.get(4), ca_code = br.get(4), bps_code = br.get(3);
 	if(br.get(1) != 0) { M.status = DEC_BAD_HEADER; meta[f] = M; return; }
+	unsigned long long number = 0;
 	{   // UTF-8 coded frame/sample number
 		const uint32_t first = br.get(8);
 		int n;
-		if(!(first & 0x80)) n = 0;
-		else if((first & 0xE0) == 0xC0) n = 1;
-		else if((first & 0xF0) == 0xE0) n = 2;
-		else if((first & 0xF8) == 0xF0) n = 3;
-		else if((first & 0xFC) == 0xF8) n = 4;
-		else if((first & 0xFE) == 0xFC) n = 5;
-		else if(first == 0xFE && variable) n = 6;
+		if(!(first & 0x80)) { n = 0; number = first; }
+		else if((first & 0xE0) == 0xC0) { n = 1; number = first & 0x1F; }
+		else if((first & 0xF0) == 0xE0) { n = 2; number = first & 0x0F; }
+		else if((first & 0xF8) == 0xF0) { n = 3; number = first & 0x07; }
+		else if((first & 0xFC) == 0xF8) { n = 4; number = first & 0x03; }
+		else if((first & 0xFE) == 0xFC) { n = 5; number = first & 0x01; }
+		else if(first == 0xFE && variable) { n = 6; number = 0; }
 		else { M.status = DEC_BAD_HEADER; meta[f] = M; return; }
-		for(int k = 0; k < n; k++)
-			if((br.get(8) & 0xC0) != 0x80) { M.status = DEC_BAD_HEADER; meta[f] = M; return; }
+		for(int k = 0; k < n; k++) {
+			const uint32_t b = br.get(8);
+			if((b & 0xC0) != 0x80) { M.status = DEC_BAD_HEADER; meta[f] = M; return; }
+			number = (number << 6) | (b & 0x3F);
+		}
 	}
 	uint32_t blocksize;
 	switch(bs_code) {
@@ -278,14 +232,22 @@ __global__ void __launch_bounds__(64) k_dec_parse(DecK P, const uint8_t *__restr
 		case 7: blocksize = br.get(16) + 1; break;
 		default: blocksize = 256u << (bs_code - 8); break;
 	}
-	if(sr_code == 12) (void)br.get(8);
-	else if(sr_code == 13 || sr_code == 14) (void)br.get(16);
-	else if(sr_code == 15) { M.status = DEC_BAD_HEADER; meta[f] = M; return; }
+	uint32_t rate = (uint32_t)P.sample_rate;
+	switch(sr_code) {
+		case 0: break;
+		case 1: rate = 88200; break; case 2: rate = 176400; break; case 3: rate = 192000; break; case 4: rate = 8000; break;
+		case 5: rate = 16000; break; case 6: rate = 22050; break; case 7: rate = 24000; break; case 8: rate = 32000; break;
+		case 9: rate = 44100; break; case 10: rate = 48000; break; case 11: rate = 96000; break;
+		case 12: rate = br.get(8) * 1000u; break;
+		case 13: rate = br.get(16); break;
+		case 14: rate = br.get(16) * 10u; break;
+		default: M.status = DEC_BAD_HEADER; meta[f] = M; return;
+	}
 	{   // CRC-8 over the header bytes (crc.c:39-76)
 		const uint32_t nb = (br.pos - start) >> 3;
 		const uint8_t *p = frames + off;
 		uint32_t crc = 0;
-		for(uint32_t b = 0; b < nb; b++) {
+		for(uint32_t b = 0; b < nb && b < len; b++) {
 			crc ^= p[b];
 			for(int j = 0; j < 8; j++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xffu : (crc << 1) & 0xffu;
 		}
@@ -302,24 +264,321 @@ __global__ void __launch_bounds__(64) k_dec_parse(DecK P, const uint8_t *__restr
 		case 5: bps = 20; break; case 6: bps = 24; break; case 7: bps = 32; break;
 		default: M.status = DEC_BAD_HEADER; meta[f] = M; return;
 	}
-	M.blocksize = blocksize; M.channel_assignment = ca; M.channels = channels;
+	M.blocksize = blocksize; M.channel_assignment = ca; M.channels = channels; M.frame_number_lo = (uint32_t)number; M.variable = variable; M.sample_rate = rate;
 	if(blocksize > (uint32_t)P.blocksize || channels != (uint32_t)P.channels || bps != (uint32_t)P.bps || bps > 24) {
 		M.status = (bps > 24) ? DEC_UNSUPPORTED : DEC_MISMATCH;
 		meta[f] = M;
 		return;
 	}
-	int32_t *base = scratch + (size_t)f * P.channels * P.bs_stride;
+
+	// ---- measure subframes 0 .. channels-2 (the last one is measured by the lane that decodes it)
 	for(uint32_t c = 0; c < channels; c++) {
+		M.sub_bit[c] = br.pos - start;
 		uint32_t sub_bps = bps;
 		if((ca == 1 && c == 1) || (ca == 2 && c == 0) || (ca == 3 && c == 1)) sub_bps++;
-		if(!decode_subframe(br, blocksize, sub_bps, base + (size_t)c * P.bs_stride)) { M.status = DEC_PARSE; meta[f] = M; return; }
+		const SubHdr h = read_sub_header(br, sub_bps);
+		if(h.type != 255 && h.order > M.max_order) M.max_order = h.order;
+		if(c + 1 == channels) break;  // the last subframe: only its header (for max_order) is looked at here
+		bool ok = h.type != 255;
+		if(ok && h.type == 0) br.skip(h.bps);
+		else if(ok && h.type == 1) br.skip(blocksize * h.bps);
+		else if(ok) {
+			if(blocksize <= h.order) ok = false;
+			else {
+				br.skip(h.order * h.bps);
+				if(h.type == 3) {
+					const uint32_t prec = br.get(4);
+					if(prec == 15) ok = false;
+					br.skip(5 + h.order * (prec + 1));
+				}
+			}
+			if(ok) {
+				// stream_decoder.c:3299-3357 read_residual_partitioned_rice_, lengths only
+				const uint32_t method = br.get(2);
+				const uint32_t plen = method ? kRice2ParamLen : kRiceParamLen, pesc = method ? kRice2Escape : kRiceEscape;
+				const uint32_t po = br.get(4);
+				const uint32_t psamples = blocksize >> po;
+				if(method > 1 || (po > 0 ? (psamples < h.order || (psamples << po) != blocksize) : blocksize < h.order)) ok = false;
+				uint32_t i = h.order;
+				for(uint32_t p = 0; ok && p < (1u << po); p++) {
+					const uint32_t k = br.get(plen);
+					const uint32_t pend = (po == 0) ? blocksize : (p + 1) * psamples;
+					if(k >= pesc) {
+						const uint32_t raw = br.get(5);
+						br.skip(raw * (pend - i));
+						i = pend;
+					}
+					else {
+						for(; i < pend; i++) {
+							// one Rice code: zeros, a one, k low bits
+							uint32_t v = br.peek32();
+							if(v != 0 && (uint32_t)__clz((int)v) + 1 + k <= 32u) br.consume((uint32_t)__clz((int)v) + 1 + k);
+							else { (void)br.unary(); br.skip(k); }
+						}
+					}
+					if(br.overrun()) ok = false;
+				}
+			}
+		}
+		if(!ok || br.overrun()) { M.status = DEC_PARSE; break; }
 	}
-	// zero padding to a byte boundary, then the CRC-16 footer must end exactly at the frame end
-	const uint32_t consumed_bits = ((br.pos - start) + 7) & ~7u;
-	if(consumed_bits + 16 != len * 8) M.status = DEC_LENGTH;
 	meta[f] = M;
 }
 
+// ================================================================ k_dec_frames
+// One lane per (frame, channel); CHL lanes per frame (channels rounded up to a power of two), 32 / CHL frames per warp.
+// The lanes run in lock step over the sample index i; sample i of a lane lives in history slot i % MAXORD, and the loop
+// is unrolled MAXORD times so that every history access has a compile-time register index.
+template <int MAXORD, bool WIDE>
+__device__ __forceinline__ void dec_lane_loop(BitRd &br, const bool live, const uint32_t bs_lane, const uint32_t bs_max, const uint32_t type,
+                                              const uint32_t order, const uint32_t sbps, const uint32_t wasted, const int shift, const bool lane_wide,
+                                              const int (&q)[MAXORD], const int (&warm)[MAXORD], const int32_t cval, const uint32_t po, const uint32_t plen,
+                                              const uint32_t pesc, int32_t *__restrict__ dst, const uint32_t ch, const uint32_t ca, const uint32_t cidx,
+                                              const uint32_t out_bps, bool &bad)
+{
+	int H[MAXORD];
+#pragma unroll
+	for(int j = 0; j < MAXORD; j++) H[j] = 0;
+	const uint32_t psamples = po ? (bs_lane >> po) : bs_lane;
+	uint32_t next_part = order, k = 0, raw = 0;
+	bool esc = false;
+	const int32_t lim = (int32_t)1 << (out_bps - 1);
+#pragma unroll 1
+	for(uint32_t i0 = 0; i0 < bs_max; i0 += MAXORD) {
+#pragma unroll
+		for(int u = 0; u < MAXORD; u++) {
+			const uint32_t i = i0 + (uint32_t)u;
+			const bool on = live && i < bs_lane;
+			int32_t x = 0;
+			if(on) {
+				if(type == 0) x = cval;                                   // CONSTANT
+				else if(type == 1) x = br.get_signed(sbps);              // VERBATIM
+				else if(i < order) x = warm[u];                          // warm-up (only in the first MAXORD samples)
+				else {
+					if(i == next_part) {                                  // a partition starts: parameter (+ escape width)
+						k = br.get(plen);
+						esc = k >= pesc;
+						if(esc) raw = br.get(5);
+						next_part = po ? (i / psamples + 1) * psamples : bs_lane;
+					}
+					int32_t r;
+					if(!esc) {
+						// deduplication/bitreader_read_rice_signed_block.c: unary MSBs, k LSBs, zig-zag
+						const uint32_t v = br.peek32();
+						uint32_t uu;
+						const uint32_t z = (uint32_t)__clz((int)v);
+						if(v != 0 && z + 1 + k <= 32u) {
+							uu = (z << k) | ((v << (z + 1)) >> (32u - k - (k == 0)) >> (k == 0));
+							br.consume(z + 1 + k);
+						}
+						else {
+							const uint32_t msbs = br.unary();
+							uu = (msbs << k) | (k ? br.get(k) : 0u);
+						}
+						r = (int32_t)(uu >> 1) ^ -(int32_t)(uu & 1u);
+					}
+					else r = raw ? br.get_signed(raw) : 0;
+					// prediction from the last `order` samples: x[i-1-j] sits in slot (u - 1 - j) mod MAXORD
+					int32_t pred;
+					if(WIDE && lane_wide) {
+						long long s0 = 0, s1 = 0;
+#pragma unroll
+						for(int j = 0; j < MAXORD; j += 2) {
+							s0 += (long long)q[j] * (long long)H[(u - 1 - j + 2 * MAXORD) % MAXORD];
+							if(j + 1 < MAXORD) s1 += (long long)q[j + 1] * (long long)H[(u - 2 - j + 2 * MAXORD) % MAXORD];
+						}
+						pred = (int32_t)((s0 + s1) >> shift);
+					}
+					else {
+						int s0 = 0, s1 = 0;
+#pragma unroll
+						for(int j = 0; j < MAXORD; j += 2) {
+							s0 += q[j] * H[(u - 1 - j + 2 * MAXORD) % MAXORD];
+							if(j + 1 < MAXORD) s1 += q[j + 1] * H[(u - 2 - j + 2 * MAXORD) % MAXORD];
+						}
+						pred = (s0 + s1) >> shift;
+					}
+					x = r + pred;
+				}
+				H[u] = x;
+			}
+			// ---- undo the channel decorrelation (stream_decoder.c:3476-3527) and store interleaved
+			const int32_t val = (int32_t)((uint32_t)x << wasted);
+			int32_t out = val;
+			if(ch == 2) {
+				const int32_t other = __shfl_xor_sync(0xffffffffu, val, 1);
+				if(ca == 1) out = cidx == 0 ? val : other - val;                       // left, side -> right = left - side
+				else if(ca == 2) out = cidx == 0 ? val + other : val;                  // side, right -> left = side + right
+				else if(ca == 3) {
+					const int32_t mid = cidx == 0 ? val : other, side = cidx == 0 ? other : val;
+					const int32_t m2 = (int32_t)(((uint32_t)mid << 1) | ((uint32_t)side & 1u));
+					out = cidx == 0 ? (m2 + side) >> 1 : (m2 - side) >> 1;
+				}
+			}
+			if(on) {
+				if(out < -lim || out >= lim) bad = true;  // stream_decoder.c:2458-2472 OUT_OF_BOUNDS
+				dst[(size_t)i * ch] = out;
+			}
+		}
+	}
+}
+
+template <int MAXQ>
+__global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets, int nframes,
+                                                   DecFrameMeta *__restrict__ meta, int32_t *__restrict__ pcm, unsigned long long capacity_samples,
+                                                   uint32_t *__restrict__ status_out, DecSubframeInfo *__restrict__ subinfo)
+{
+	const int ch = P.channels;
+	const int chl = ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : 8;
+	const int fpw = 32 / chl;  // frames per warp
+	const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const int f = warp_global * fpw + lane / chl;
+	const uint32_t cidx = (uint32_t)(lane % chl);
+	if(warp_global * fpw >= nframes) return;  // whole warp idle
+	const bool have = f < nframes && (int)cidx < ch;
+	DecFrameMeta M;
+	M.status = DEC_LENGTH; M.blocksize = 0; M.channel_assignment = 0; M.channels = 0;
+	unsigned long long off = 0;
+	uint32_t len = 0;
+	if(f < nframes) {
+		M = meta[f];
+		off = offsets[f];
+		len = (uint32_t)(offsets[f + 1] - off);
+	}
+	const unsigned long long first = (unsigned long long)f * (unsigned long long)P.blocksize;
+	// this instantiation's share of the frames: MAXQ = 12 takes every frame whose predictors have at most 12 taps, MAXQ = 32 the rest
+	const bool mine = (MAXQ == 12) ? M.max_order <= 12 : M.max_order > 12;
+	if(!__any_sync(0xffffffffu, f < nframes && (mine || M.status != DEC_OK))) return;
+	const bool report = f < nframes && (MAXQ == 12 ? (mine || M.status != DEC_OK) : (mine && M.status == DEC_OK));
+	bool live = have && mine && M.status == DEC_OK && first + M.blocksize <= capacity_samples;
+	const bool fits = !(have && mine && M.status == DEC_OK) || live;
+	const uint32_t bs_lane = live ? M.blocksize : 0u;
+	const uint32_t ca = M.channel_assignment;
+	const uint32_t bps = (uint32_t)P.bps;
+	uint32_t sub_bps = bps;
+	if((ca == 1 && cidx == 1) || (ca == 2 && cidx == 0) || (ca == 3 && cidx == 1)) sub_bps++;
+
+	// ---- per-lane set-up: subframe header, warm-up samples, predictor (stream_decoder.c:2949-3297)
+	BitRd br;
+	br.init(frames + off, live ? len : 0u, live ? M.sub_bit[cidx < FB200_MAX_CHANNELS ? cidx : 0] : 0u);
+	const uint32_t lead = br.pos - (live ? M.sub_bit[cidx < FB200_MAX_CHANNELS ? cidx : 0] : 0u);
+	SubHdr h;
+	h.type = 255; h.order = 0; h.wasted = 0; h.bps = sub_bps; h.precision = 0; h.shift = 0;
+	bool bad = false;
+	if(live) {
+		h = read_sub_header(br, sub_bps);
+		if(h.type == 255 || (h.type >= 2 && bs_lane <= h.order) || h.order > (uint32_t)MAXQ) { bad = true; h.type = 0; h.order = 0; }
+	}
+	const uint32_t order = live ? h.order : 0u;
+	// the widest predictor in the warp picks the instantiation (warp-uniform)
+	uint32_t omax = order;
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) omax = max(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+	uint32_t bs_max = bs_lane;
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) bs_max = max(bs_max, __shfl_xor_sync(0xffffffffu, bs_max, o));
+
+	int32_t cval = 0;
+	int qbuf[MAXQ], wbuf[MAXQ];
+#pragma unroll
+	for(int j = 0; j < MAXQ; j++) { qbuf[j] = 0; wbuf[j] = 0; }
+	uint32_t po = 0, method = 0;
+	bool lane_wide = false;
+	if(live && !bad) {
+		if(h.type == 0) cval = br.get_signed(h.bps);
+		else if(h.type >= 2) {
+#pragma unroll
+			for(int j = 0; j < MAXQ; j++)
+				if(j < (int)order) wbuf[j] = br.get_signed(h.bps);
+			if(h.type == 3) {
+				const uint32_t prec = br.get(4);
+				if(prec == 15) bad = true;
+				h.precision = prec + 1;
+				h.shift = br.get_signed(5);
+				if(h.shift < 0) bad = true;
+				uint32_t abs_sum = 0;
+#pragma unroll
+				for(int j = 0; j < MAXQ; j++)
+					if(j < (int)order) { qbuf[j] = br.get_signed(h.precision); abs_sum += (uint32_t)abs(qbuf[j]); }
+				// variant rule of stream_decoder.c:3243-3247 (lpc.c:942-968)
+				const unsigned long long max_abs = 1ull << (h.bps - 1);
+				const unsigned long long max_pred = max_abs * abs_sum;
+				const unsigned long long max_after = (unsigned long long)(-1 * ((-1 * (long long)max_pred) >> (h.shift < 0 ? 0 : h.shift)));
+				lane_wide = !(dec_silog2((long long)(max_abs + max_after)) <= 32 && dec_silog2((long long)max_pred) <= 32);
+			}
+			else {
+				// fixed predictors as taps (fixed.c:571-629); 32-bit arithmetic agrees with the reference's for bps <= 25
+				const int tab[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+#pragma unroll
+				for(int j = 0; j < 4; j++) qbuf[j] = tab[order][j];
+			}
+			method = br.get(2);
+			po = br.get(4);
+			const uint32_t psamples = bs_lane >> po;
+			if(method > 1 || (po > 0 ? (psamples < order || (psamples << po) != bs_lane) : bs_lane < order)) bad = true;
+		}
+		if(br.overrun()) bad = true;
+	}
+	if(bad) live = false;  // a broken subframe decodes nothing; its partner lanes still run (the frame is reported bad)
+	if(subinfo && have && report) {
+		DecSubframeInfo &I = subinfo[(size_t)f * ch + cidx];
+		I.type = (uint8_t)(h.type == 255 ? 0 : h.type); I.order = (uint8_t)order; I.wasted = (uint8_t)h.wasted; I.precision = (uint8_t)h.precision;
+		I.shift = (int8_t)h.shift; I.method = (uint8_t)method; I.porder = (uint8_t)po; I.pad = 0;
+		for(int j = 0; j < FB200_MAX_LPC_ORDER; j++) { I.qlp[j] = (h.type == 3 && j < MAXQ) ? qbuf[j < MAXQ ? j : 0] : 0; I.warmup[j] = j < MAXQ ? wbuf[j < MAXQ ? j : 0] : 0; }
+		if(h.type == 0) I.warmup[0] = cval;
+	}
+	const uint32_t plen = method ? kRice2ParamLen : kRiceParamLen, pesc = method ? kRice2Escape : kRiceEscape;
+	const int shift = h.type == 3 ? h.shift : 0;
+	int32_t *dst = pcm + (size_t)first * ch + cidx;
+	const bool any_wide = __any_sync(0xffffffffu, lane_wide && live);
+	const uint32_t bs_eff = live ? bs_lane : 0u;
+	const uint32_t ltype = live ? h.type : 0u;
+
+#define FB200_DEC_RUN(MO)                                                                                                                    \
+	do {                                                                                                                                       \
+		int q[MO], w[MO];                                                                                                                      \
+		_Pragma("unroll") for(int j = 0; j < MO; j++) { q[j] = qbuf[j < MAXQ ? j : 0]; w[j] = wbuf[j < MAXQ ? j : 0]; }                                                     \
+		if(any_wide) dec_lane_loop<MO, true>(br, live, bs_eff, bs_max, ltype, order, h.bps, h.wasted, shift, lane_wide, q, w, cval, po, plen,   \
+		                                     pesc, dst, (uint32_t)ch, ca, cidx, bps, bad);                                                     \
+		else dec_lane_loop<MO, false>(br, live, bs_eff, bs_max, ltype, order, h.bps, h.wasted, shift, false, q, w, cval, po, plen, pesc, dst,    \
+		                              (uint32_t)ch, ca, cidx, bps, bad);                                                                       \
+	} while(0)
+	if(MAXQ == 12) {
+		if(omax <= 8) FB200_DEC_RUN(8);
+		else FB200_DEC_RUN(12);
+	}
+	else FB200_DEC_RUN(MAXQ);
+#undef FB200_DEC_RUN
+
+	// ---- frame end: padding to a byte boundary + CRC-16 must end at (or, in index mode, before) the given end
+	uint32_t status = M.status;
+	uint32_t frame_bytes = 0;
+	if(have && mine && M.status == DEC_OK) {
+		if(!fits) status = DEC_LENGTH;
+		if(br.overrun()) bad = true;
+		if((int)cidx == ch - 1 && live) {
+			const uint32_t consumed = (br.pos - lead + 7) >> 3;
+			frame_bytes = consumed + 2;
+			if(P.loose_end ? frame_bytes > len : frame_bytes != len) status = DEC_LENGTH;
+		}
+	}
+	// fold the lanes of a frame: any bad subframe makes the frame bad; the last channel's lane knows the length
+	uint32_t badmask = (have && bad) ? 1u : 0u, st = status, fb = frame_bytes;
+	for(int o = 1; o < chl; o <<= 1) {
+		badmask |= __shfl_xor_sync(0xffffffffu, badmask, o);
+		const uint32_t so = __shfl_xor_sync(0xffffffffu, st, o);
+		st = st != DEC_OK ? st : so;
+		fb = max(fb, __shfl_xor_sync(0xffffffffu, fb, o));
+	}
+	if(report && cidx == 0) {
+		if(st == DEC_OK && badmask) st = DEC_PARSE;
+		meta[f].status = st;
+		meta[f].frame_bytes = fb;
+		if(status_out && st != DEC_OK) status_out[f] = st | (M.blocksize << 8);  // good frames get theirs after the CRC-16 check
+	}
+}
+
+// ================================================================ k_dec_crc
 // GF(2)[x] multiply mod x^16+x^15+x^2+1
 __device__ __forceinline__ uint32_t dec_gf16_mul(uint32_t a, uint32_t b)
 {
@@ -332,9 +591,11 @@ __device__ __forceinline__ uint32_t dec_gf16_mul(uint32_t a, uint32_t b)
 	return r;
 }
 
-// One warp per frame; lane l owns a contiguous chunk aligned to the end of the frame.
+// One warp per frame; lane l owns a contiguous chunk of bytes aligned to the end of the frame. Byte table in shared memory,
+// the tail of the chunk loop reads whole words when the frame start is word aligned... kept byte-wise: the frames of a
+// stream start at arbitrary byte offsets. Writes the final per-frame status word.
 __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets,
-                                                int nframes, DecFrameMeta *__restrict__ meta)
+                                                int nframes, DecFrameMeta *__restrict__ meta, uint32_t *__restrict__ status_out)
 {
 	__shared__ uint16_t s_tab[256];
 	for(int e = threadIdx.x; e < 256; e += blockDim.x) {
@@ -346,8 +607,10 @@ __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t *__restrict__ fra
 	__syncthreads();
 	const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
 	if(f >= nframes) return;
+	const DecFrameMeta M = meta[f];
+	if(M.status != DEC_OK) return;
 	const unsigned long long off = offsets[f];
-	const uint32_t len = (uint32_t)(offsets[f + 1] - off);
+	const uint32_t len = M.frame_bytes;
 	if(len < 3) return;
 	const uint32_t nbytes = len - 2;
 	const uint8_t *p = frames + off;
@@ -371,46 +634,9 @@ __global__ void __launch_bounds__(128) k_dec_crc(const uint8_t *__restrict__ fra
 	}
 	if(lane == 0) {
 		const uint32_t want = ((uint32_t)p[nbytes] << 8) | p[nbytes + 1];
-		if(crc != want && meta[f].status == DEC_OK) meta[f].status = DEC_CRC16;
-	}
-}
-
-// Undo the inter-channel decorrelation and interleave (stream_decoder.c:3476-3527).
-__global__ void __launch_bounds__(256) k_dec_merge(DecK P, const int32_t *__restrict__ scratch, const DecFrameMeta *__restrict__ meta,
-                                                  int32_t *__restrict__ pcm, unsigned long long capacity_samples, uint32_t *__restrict__ status_out)
-{
-	const int f = blockIdx.x;
-	const DecFrameMeta M = meta[f];
-	if(threadIdx.x == 0 && status_out) status_out[f] = M.status | (M.blocksize << 8);  // low byte: status, upper: decoded blocksize
-	if(M.status != DEC_OK) return;
-	const int bs = (int)M.blocksize, ch = P.channels;
-	const unsigned long long first = (unsigned long long)f * P.blocksize;
-	if(first + bs > capacity_samples) return;
-	const int32_t *src = scratch + (size_t)f * ch * P.bs_stride;
-	int32_t *dst = pcm + first * ch;
-	if(ch == 2) {
-		int2 *d2 = reinterpret_cast<int2 *>(dst);
-		for(int i = threadIdx.x; i < bs; i += blockDim.x) {
-			const int32_t a = src[i], b = src[P.bs_stride + i];
-			int32_t l, r;
-			switch(M.channel_assignment) {
-				case 1: l = a; r = a - b; break;                 // left/side
-				case 2: l = a + b; r = b; break;                 // right/side  (a = side)
-				case 3: {                                         // mid/side
-					const int32_t mid = (int32_t)(((uint32_t)a << 1) | ((uint32_t)b & 1u));
-					l = (mid + b) >> 1; r = (mid - b) >> 1;
-					break;
-				}
-				default: l = a; r = b; break;
-			}
-			d2[i] = make_int2(l, r);
-		}
-	}
-	else {
-		for(int i = threadIdx.x; i < bs * ch; i += blockDim.x) {
-			const int s = i / ch, c = i - s * ch;
-			dst[i] = src[(size_t)c * P.bs_stride + s];
-		}
+		uint32_t st = DEC_OK;
+		if(crc != want) { st = DEC_CRC16; meta[f].status = DEC_CRC16; }
+		if(status_out) status_out[f] = st | (M.blocksize << 8);  // low byte: status, upper: decoded blocksize
 	}
 }
 

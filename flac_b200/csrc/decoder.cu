@@ -12,8 +12,10 @@ struct fb200_decoder {
 	int device = 0;
 	uint32_t max_frames = 0;
 	DecK k{};
-	int32_t *d_scratch = nullptr;
 	DecFrameMeta *d_meta = nullptr;
+	DecSubframeInfo *d_subinfo = nullptr;  // per (frame, channel), only when the client asked for subframe details
+	size_t d_subinfo_cap = 0;
+	bool want_subinfo = false;
 	// staging for the host entry point
 	uint8_t *d_frames = nullptr;
 	size_t d_frames_cap = 0;
@@ -81,9 +83,8 @@ int fb200_decoder_create(const fb200_decoder_config *cfg, int device, uint32_t m
 	d->max_frames = max_frames ? max_frames : 16384;
 	d->k.channels = (int)cfg->channels; d->k.bps = (int)cfg->bits_per_sample; d->k.sample_rate = (int)cfg->sample_rate;
 	d->k.blocksize = (int)cfg->blocksize;
-	d->k.bs_stride = ((int)cfg->blocksize + 3) / 4 * 4;
-	if(cudaMalloc(&d->d_scratch, (size_t)d->max_frames * cfg->channels * d->k.bs_stride * sizeof(int32_t)) != cudaSuccess ||
-	   cudaMalloc(&d->d_meta, (size_t)d->max_frames * sizeof(DecFrameMeta)) != cudaSuccess ||
+	d->k.loose_end = 0;
+	if(cudaMalloc(&d->d_meta, (size_t)d->max_frames * sizeof(DecFrameMeta)) != cudaSuccess ||
 	   cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
 		set_error("decoder workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
 		fb200_decoder_destroy(d);
@@ -97,7 +98,7 @@ void fb200_decoder_destroy(fb200_decoder *d)
 {
 	if(!d) return;
 	cudaSetDevice(d->device);
-	cudaFree(d->d_scratch); cudaFree(d->d_meta); cudaFree(d->d_frames); cudaFree(d->d_offsets); cudaFree(d->d_pcm); cudaFree(d->d_status);
+	cudaFree(d->d_subinfo); cudaFree(d->d_meta); cudaFree(d->d_frames); cudaFree(d->d_offsets); cudaFree(d->d_pcm); cudaFree(d->d_status);
 	if(d->stream) cudaStreamDestroy(d->stream);
 	delete d;
 }
@@ -133,20 +134,35 @@ int fb200_decode_device(fb200_decoder *d, const uint8_t *d_frames, const uint64_
 	FB_CUDA(cudaSetDevice(d->device));
 	cudaStream_t st = (cudaStream_t)cuda_stream;
 	const unsigned long long *offs = reinterpret_cast<const unsigned long long *>(d_frame_offsets);
+	const int ch = (int)d->cfg.channels;
+	const int chl = ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : 8;
+	const int fpw = 32 / chl;
+	if(d->want_subinfo && (size_t)nframes * ch > d->d_subinfo_cap) {
+		cudaFree(d->d_subinfo); d->d_subinfo = nullptr; d->d_subinfo_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_subinfo, (size_t)nframes * ch * sizeof(DecSubframeInfo)));
+		d->d_subinfo_cap = (size_t)nframes * ch;
+	}
 	uint32_t done = 0;
 	while(done < nframes) {
 		const int nf = (int)((nframes - done) < d->max_frames ? (nframes - done) : d->max_frames);
-		// offsets are absolute into d_frames; output frame index is absolute too (done + i)
+		// offsets are absolute into d_frames; frame `done + i` decodes to sample offset (done + i) * blocksize
+		const unsigned long long used = (unsigned long long)done * d->cfg.blocksize;
+		const unsigned long long cap_left = pcm_capacity_samples > used ? pcm_capacity_samples - used : 0ull;  // frames that do not fit are reported (DEC_LENGTH), never written
 		dprof_mark(d, -1, st);
-		k_dec_parse<<<(nf + 63) / 64, 64, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_scratch, d->d_meta);
-		dprof_mark(d, FB200_DPROF_PARSE, st);
-		k_dec_crc<<<(nf + 3) / 4, 128, 0, st>>>(d_frames, offs + done, nf, d->d_meta);
+		k_dec_walk<<<(nf + 127) / 128, 128, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_meta);
+		dprof_mark(d, FB200_DPROF_WALK, st);
+		const int warps = (nf + fpw - 1) / fpw;
+		// predictors of at most 12 taps (every preset) and the rest (-l 13..32): two instantiations, each taking its frames
+		k_dec_frames<12><<<(warps + 3) / 4, 128, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
+		                                                 d_frame_status ? d_frame_status + done : nullptr,
+		                                                 d->want_subinfo ? d->d_subinfo + (size_t)done * ch : nullptr);
+		k_dec_frames<32><<<(warps + 3) / 4, 128, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
+		                                                 d_frame_status ? d_frame_status + done : nullptr,
+		                                                 d->want_subinfo ? d->d_subinfo + (size_t)done * ch : nullptr);
+		dprof_mark(d, FB200_DPROF_FRAMES, st);
+		k_dec_crc<<<(nf + 3) / 4, 128, 0, st>>>(d_frames, offs + done, nf, d->d_meta, d_frame_status ? d_frame_status + done : nullptr);
 		dprof_mark(d, FB200_DPROF_CRC, st);
-		k_dec_merge<<<nf, 256, 0, st>>>(d->k, d->d_scratch, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * d->cfg.channels,
-		                               pcm_capacity_samples - (unsigned long long)done * d->cfg.blocksize,
-		                               d_frame_status ? d_frame_status + done : nullptr);
-		dprof_mark(d, FB200_DPROF_MERGE, st);
-		d->launches += 3;
+		d->launches += 4;
 		done += nf;
 	}
 	FB_CUDA(cudaGetLastError());

@@ -181,6 +181,9 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t b)
 // generated with gf16_mul by repeated squaring from x = 0x2.
 __device__ __constant__ const uint16_t kCrcXPow2[15] = {0x2, 0x4, 0x10, 0x100, 0x8005, 0x8017, 0x8113, 0x106, 0x8011, 0x8107, 0x16, 0x114, 0x8115, 0x112, 0x8101};
 
+// x^(8k) mod (x^8+x^2+x+1), k = 0..15: weights that combine per-byte CRC-8s of a frame header (crc.c:39-76)
+__device__ __constant__ const uint8_t kCrc8XPow8[16] = {0x01, 0x07, 0x15, 0x6b, 0x16, 0x62, 0x29, 0xdf, 0x13, 0x79, 0x68, 0x1f, 0x5d, 0x94, 0xe5, 0xb5};
+
 // fixed predictors as FIR taps (fixed.c:470-530): r = x[i] - sum_j c[j] x[i-1-j]
 __device__ __forceinline__ int fixed_tap(int order, int j)
 {

@@ -45,6 +45,23 @@ __global__ void k_crc16_tables(uint16_t *__restrict__ tab)
 		prev = ((prev << 8) & 0xffffu) ^ tab[prev >> 8];
 		tab[k * 256 + b] = (uint16_t)prev;
 	}
+	// combine multipliers: tab[1024 + (Lw >> 1) * 9 + s] = x^(32 Lw 2^s) mod (x^16+x^15+x^2+1) for odd Lw < 64, s < 9
+	for(int idx = b; idx < kCrcLwRows * 9; idx += blockDim.x) {
+		const uint32_t Lw = 2u * (uint32_t)(idx / 9) + 1u;
+		unsigned long long e = (32ull * Lw) << (idx % 9);
+		uint32_t m = 1;
+		for(int j = 0; e; j++, e >>= 1)
+			if(e & 1ull) m = gf16_mul(m, kCrcXPow2[j % 15]);
+		tab[1024 + idx] = (uint16_t)m;
+	}
+	__syncthreads();
+	// nibble products: tab[kCrcMulBase + ((row * 9 + s) * 4 + pos) * 16 + n] = (n << 4 pos) * x^(32 Lw 2^s): a GF(2^16) product by a
+	// level multiplier becomes four 16-entry lookups instead of a 16-step shift-and-add
+	for(int idx = b; idx < kCrcLwRows * 9 * 64; idx += blockDim.x) {
+		const uint32_t m = tab[1024 + idx / 64];
+		const uint32_t pos = (uint32_t)(idx >> 4) & 3u, n = (uint32_t)idx & 15u;
+		tab[kCrcMulBase + idx] = (uint16_t)gf16_mul(n << (4 * pos), m);
+	}
 }
 
 // decoupled look-back status word: value << 24 | epoch (22 bits) << 2 | flag (1 aggregate, 2 inclusive prefix)
@@ -234,47 +251,68 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 	else if(frame_number < 0x4000000) utf8_len = 5;
 	else utf8_len = 6;
 	const uint32_t header_bits = 32 + 8 * utf8_len + (bs_hint ? (bs_hint == 6 ? 8 : 16) : 0) + (sr_hint ? (sr_hint == 12 ? 8 : 16) : 0) + 8;
-	uint32_t hdr[4] = {0, 0, 0, 0};  // header bytes, big-endian words, left aligned
-	if(tid == 0) {
-		uint32_t nb8 = 0, crc = 0;
-		auto push = [&](uint32_t byte) {
-			// append one byte (128-bit shift register) and run it through CRC-8, poly 0x07 (crc.c:39-76)
-			hdr[0] = (hdr[0] << 8) | (hdr[1] >> 24); hdr[1] = (hdr[1] << 8) | (hdr[2] >> 24);
-			hdr[2] = (hdr[2] << 8) | (hdr[3] >> 24); hdr[3] = (hdr[3] << 8) | (byte & 0xffu);
-			nb8++;
-			crc ^= byte & 0xffu;
-#pragma unroll
-			for(int j = 0; j < 8; j++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xffu : (crc << 1) & 0xffu;
-		};
+	if(warp == (NT >> 5) - 1) {
+		// one header byte per lane; CRC-8 (poly 0x07, crc.c:39-76) of the whole header from per-byte CRCs weighted by
+		// x^(8 * bytes behind) -- no serial loop over the header
+		const int nb8 = (int)(header_bits >> 3);  // bytes including the CRC-8
+		const int pos_bs = 4 + (int)utf8_len;
+		const int bs_bytes = bs_hint ? (bs_hint == 6 ? 1 : 2) : 0;
+		const int pos_sr = pos_bs + bs_bytes;
+		const int sr_bytes = sr_hint ? (sr_hint == 12 ? 1 : 2) : 0;
 		uint32_t ca_code;
 		switch(ca) { case 0: ca_code = (uint32_t)P.channels - 1; break; case 1: ca_code = 8; break; case 2: ca_code = 9; break; default: ca_code = 10; break; }
 		uint32_t bps_code;
 		switch(P.bps) { case 8: bps_code = 1; break; case 12: bps_code = 2; break; case 16: bps_code = 4; break; case 20: bps_code = 5; break; case 24: bps_code = 6; break; case 32: bps_code = 7; break; default: bps_code = 0; break; }
-		push(0xff); push(0xf8);  // sync 0x3ffe, reserved 0, fixed-blocksize stream
-		push((bs_code << 4) | sr_code);
-		push((ca_code << 4) | (bps_code << 1));
-		const uint32_t v = frame_number;  // UTF-8 style frame number (bitwriter.c:832-933)
-		switch(utf8_len) {
-			case 1: push(v); break;
-			case 2: push(0xC0 | (v >> 6)); break;
-			case 3: push(0xE0 | (v >> 12)); break;
-			case 4: push(0xF0 | (v >> 18)); break;
-			case 5: push(0xF8 | (v >> 24)); break;
-			default: push(0xFC | (v >> 30)); break;
+		const uint32_t v = frame_number;
+		uint32_t byte = 0;
+		const int i = lane;
+		if(i == 0) byte = 0xff;                                   // sync 0x3ffe, reserved 0, fixed-blocksize stream
+		else if(i == 1) byte = 0xf8;
+		else if(i == 2) byte = (bs_code << 4) | sr_code;
+		else if(i == 3) byte = (ca_code << 4) | (bps_code << 1);
+		else if(i < pos_bs) {                                     // UTF-8 style frame number (bitwriter.c:832-933)
+			const int j = i - 4;
+			if(j == 0) {
+				switch(utf8_len) {
+					case 1: byte = v; break;
+					case 2: byte = 0xC0 | (v >> 6); break;
+					case 3: byte = 0xE0 | (v >> 12); break;
+					case 4: byte = 0xF0 | (v >> 18); break;
+					case 5: byte = 0xF8 | (v >> 24); break;
+					default: byte = 0xFC | (v >> 30); break;
+				}
+			}
+			else byte = 0x80 | ((v >> (6 * ((int)utf8_len - 1 - j))) & 0x3F);
 		}
-		for(int kq = (int)utf8_len - 2; kq >= 0; kq--) push(0x80 | ((v >> (6 * kq)) & 0x3F));
-		if(bs_hint == 6) push((uint32_t)bs - 1);
-		else if(bs_hint == 7) { push(((uint32_t)bs - 1) >> 8); push((uint32_t)bs - 1); }
-		if(sr_hint == 12) push((uint32_t)P.sample_rate / 1000);
-		else if(sr_hint == 13) { push((uint32_t)P.sample_rate >> 8); push((uint32_t)P.sample_rate); }
-		else if(sr_hint == 14) { push(((uint32_t)P.sample_rate / 10) >> 8); push((uint32_t)P.sample_rate / 10); }
-		const uint32_t c8 = crc;
-		push(c8);
-		// left-align the nb8 bytes
-		for(uint32_t r = nb8; r < 16; r++) {
-			hdr[0] = (hdr[0] << 8) | (hdr[1] >> 24); hdr[1] = (hdr[1] << 8) | (hdr[2] >> 24);
-			hdr[2] = (hdr[2] << 8) | (hdr[3] >> 24); hdr[3] = hdr[3] << 8;
+		else if(i < pos_sr) byte = ((uint32_t)bs - 1) >> (8 * (bs_bytes - 1 - (i - pos_bs)));
+		else if(i < nb8 - 1) {
+			const uint32_t sv = sr_hint == 12 ? (uint32_t)P.sample_rate / 1000 : sr_hint == 13 ? (uint32_t)P.sample_rate : (uint32_t)P.sample_rate / 10;
+			byte = sv >> (8 * (sr_bytes - 1 - (i - pos_sr)));
 		}
+		byte &= 0xffu;
+		uint32_t c = 0;
+		if(i < nb8 - 1) {
+			c = byte;
+#pragma unroll
+			for(int j = 0; j < 8; j++) c = (c & 0x80u) ? ((c << 1) ^ 0x07u) & 0xffu : (c << 1) & 0xffu;
+			// times x^(8 * (nb8 - 2 - i)) in GF(2)[x] / (x^8 + x^2 + x + 1)
+			const uint32_t wgt = kCrc8XPow8[nb8 - 2 - i];
+			uint32_t r = 0;
+#pragma unroll
+			for(int j = 7; j >= 0; j--) {
+				r = (r & 0x80u) ? ((r << 1) ^ 0x07u) & 0xffu : (r << 1) & 0xffu;
+				if((wgt >> j) & 1u) r ^= c;
+			}
+			c = r;
+		}
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+		if(i == nb8 - 1) byte = c;
+		if(i >= nb8) byte = 0;
+		uint32_t w = byte << (24 - 8 * (i & 3));
+		w |= __shfl_xor_sync(0xffffffffu, w, 1);
+		w |= __shfl_xor_sync(0xffffffffu, w, 2);
+		if((i & 3) == 0 && i < 16) S.hdr[i >> 2] = w;  // big-endian words, left aligned
 	}
 
 	// ---- zero the word buffer up to an upper bound of the frame: a Rice partition's true length exceeds its
@@ -302,14 +340,16 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 		int32_t *const p1 = planar + planar_words + kSearch4ZeroRow;
 		for(int i = tid; i < kSearch4ZeroRow; i += NT) { planar[i] = 0; if(CH == 2) planar[planar_words + i] = 0; }  // history of row 0
 		if(CH == 2) {
-			const int w0 = __ldg(&bp[sidx0].wasted), w1 = __ldg(&bp[sidx1].wasted);
-			auto pick = [](int s, int L, int R) -> int { return s == 0 ? L : s == 1 ? R : s == 2 ? ((L + R) >> 1) : (L - R); };
+			// signal = (a L + b R) >> sh: L (1,0), R (0,1), mid (1,1) >> 1, side (1,-1) (stream_encoder.c:3823-3836); the wasted-bits
+			// shift (:3842-3867) folds into sh
+			const int a0c = sidx0 != 1, b0c = sidx0 == 0 ? 0 : sidx0 == 3 ? -1 : 1, sh0 = __ldg(&bp[sidx0].wasted) + (sidx0 == 2);
+			const int a1c = sidx1 != 1, b1c = sidx1 == 0 ? 0 : sidx1 == 3 ? -1 : 1, sh1 = __ldg(&bp[sidx1].wasted) + (sidx1 == 2);
 #pragma unroll
 			for(int k = 0; k < R_T / 4; k++) {
 				const int i = 2 * (k * NT + tid);  // first of the two sample pairs in this vector
 				const int row = i / R_T, col = i - row * R_T;
-				*reinterpret_cast<int2 *>(p0 + row * 36 + col) = make_int2(pick(sidx0, rv[k].x, rv[k].y) >> w0, pick(sidx0, rv[k].z, rv[k].w) >> w0);
-				*reinterpret_cast<int2 *>(p1 + row * 36 + col) = make_int2(pick(sidx1, rv[k].x, rv[k].y) >> w1, pick(sidx1, rv[k].z, rv[k].w) >> w1);
+				*reinterpret_cast<int2 *>(p0 + row * 36 + col) = make_int2((a0c * rv[k].x + b0c * rv[k].y) >> sh0, (a0c * rv[k].z + b0c * rv[k].w) >> sh0);
+				*reinterpret_cast<int2 *>(p1 + row * 36 + col) = make_int2((a1c * rv[k].x + b1c * rv[k].y) >> sh1, (a1c * rv[k].z + b1c * rv[k].w) >> sh1);
 			}
 		}
 		else {
@@ -465,15 +505,12 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 
 	// ---- pass 2: pack
 	if(fits) {
-		if(tid == 0) {
-			// place the pre-built frame header at byte s0
+		if(warp == (NT >> 5) - 1 && lane < 5) {
+			// place the pre-built frame header at byte s0 (S.hdr was written before the barriers above)
 			const uint32_t sh = 8 * s0;
-			const uint32_t nwh = (header_bits >> 3) + 3 >> 2;
-			for(uint32_t i = 0; i <= nwh && i < 5; i++) {
-				const uint32_t hi = i > 0 ? hdr[i - 1] : 0u, lo = i < 4 ? hdr[i] : 0u;
-				const uint32_t w = sh ? __funnelshift_r(lo, hi, sh) : lo;  // bytes of hdr shifted right by s0
-				if(w) atomicOr(&words[i], w);
-			}
+			const uint32_t hi = lane > 0 ? S.hdr[lane - 1] : 0u, lo = lane < 4 ? S.hdr[lane] : 0u;
+			const uint32_t w = sh ? __funnelshift_r(lo, hi, sh) : lo;  // the header bytes shifted right by s0 bytes
+			if(w) atomicOr(&words[lane], w);
 		}
 		// subframe header fields: the first warp of a channel writes them, every field from its own lane
 		if(run < 32) {
@@ -524,31 +561,78 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 		}
 		// residual codes of this run (stream_encoder_framing.c:538-594, bitwriter.c:575-706)
 		if(predicted) {
-			RunPacker pk;
-			pk.init(words, bit0 + start + pre);
-			if(one_partition) {
-				const uint32_t k = k_run;
-				const int pidx = base / psize;
-				const int first_res = pidx == 0 ? order : pidx * psize;
+			if(one_partition && base >= order) {
+				// every sample of the run is a residual of ONE partition; the parameter field, if the partition starts here,
+				// goes first. Hot loop: zeros + stop bit + k low bits as one field of n = q + k + 1 bits; the pending word
+				// `cur` (fill bits used) spills into `words` when it completes. Only the run's first word can be shared with
+				// the previous run: it is kept in `fw` and OR-ed in at the end, so the loop has plain stores only.
+				const uint32_t k = k_run, k1 = k + 1;
 				const uint32_t stop = 1u << k, lowmask = stop - 1u;
+				uint32_t pos = bit0 + start + pre;
+				const int wfirst = (int)(pos >> 5);
+				int widx = wfirst;
+				uint32_t fill = pos & 31u, cur = 0, fw = 0;
+				bool fw_set = false;
+				auto put = [&](uint32_t val, uint32_t n) {  // 1 <= n <= 32, val < 2^n
+					const unsigned long long t = (unsigned long long)val << (64u - fill - n);
+					cur |= (uint32_t)(t >> 32);
+					fill += n;
+					if(fill >= 32u) {
+						if(widx != wfirst) words[widx] = cur;
+						else { fw = cur; fw_set = true; }
+						widx++;
+						cur = (uint32_t)t;
+						fill -= 32u;
+					}
+				};
+				{
+					const int pidx = base / psize;
+					if(base == (pidx == 0 ? order : pidx * psize)) put(k, plen);  // the partition's first residual is this run's first sample
+				}
 #pragma unroll 1
 				for(int v4 = 0; v4 < R_T / 4; v4++) {
 					const uint4 uv = *reinterpret_cast<const uint4 *>(rowp + 4 * v4);
-					const uint32_t uu[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
 					for(int e = 0; e < 4; e++) {
-						const int i = base + 4 * v4 + e;
-						if(i >= order) {
-							if(i == first_res) pk.put(k, plen);
-							const uint32_t qz = uu[e] >> k;
-							const uint32_t val = stop | (uu[e] & lowmask);
-							if(qz + k + 1 <= 32u) pk.put(val, qz + k + 1);  // zeros + stop bit + low bits as one field
-							else { pk.skip(qz); pk.put(val, k + 1); }
+						const uint32_t u = e == 0 ? uv.x : e == 1 ? uv.y : e == 2 ? uv.z : uv.w;
+						const uint32_t qz = u >> k;
+						const uint32_t val = stop | (u & lowmask);
+						if(qz + k1 <= 32u) put(val, qz + k1);
+						else {
+							// a long unary run (rare): zeros word by word, then the stop bit + low bits
+							uint32_t z = qz;
+							while(z) { const uint32_t c = z < 32u - fill ? z : 32u - fill; put(0u, c); z -= c; }
+							put(val, k1);
 						}
 					}
 				}
+				// the run's first word (shared with the previous run) and its last, partial word (shared with the next)
+				if(fw_set) { if(fw) atomicOr(&words[wfirst], fw); if(cur) atomicOr(&words[widx], cur); }
+				else if(cur) atomicOr(&words[widx], cur);
+			}
+			else if(one_partition) {
+				// the run that contains the warm-up samples / the first residual of partition 0
+				RunPacker pk;
+				pk.init(words, bit0 + start + pre);
+				const uint32_t k = k_run;
+				const uint32_t stop = 1u << k, lowmask = stop - 1u;
+#pragma unroll 1
+				for(int m = 0; m < R_T; m++) {
+					const int i = base + m;
+					if(i >= order) {
+						if(i == order) pk.put(k, plen);
+						const uint32_t u = (uint32_t)rowp[m];
+						const uint32_t qz = u >> k;
+						pk.skip(qz);
+						pk.put(stop | (u & lowmask), k + 1);
+					}
+				}
+				pk.finish();
 			}
 			else {
+				// partitions shorter than a run (partition orders above log2(bs / R_T)): the parameter changes inside the run
+				RunPacker pk;
+				pk.init(words, bit0 + start + pre);
 				int p = base / psize;
 				int next = (p + 1) * psize;
 				uint32_t k = __ldg(&pl->params[p]);
@@ -563,8 +647,8 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 						pk.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
 					}
 				}
+				pk.finish();
 			}
-			pk.finish();
 		}
 		else if(type == SF_VERBATIM) {
 			RunPacker pk;
@@ -578,14 +662,32 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 
 	// ---- CRC-16 over the frame: equal word chunks aligned to the (word aligned) end, slicing-by-4, GF(2) combine.
 	// The signals are dead: the slicing tables go where they were.
-	for(int i = tid; i < 4 * 256 / 2; i += NT) reinterpret_cast<uint32_t *>(crc_tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.crc_tab) + i);
 	int Lw = ((int)wend + NT - 1) / NT;
 	Lw |= 1;  // odd chunk length: conflict-free strided reads
+	const bool lw_tab = Lw < 2 * kCrcLwRows;
+	uint16_t *const mul_tab = crc_tab + 1024;  // [9 levels][4 nibble positions][16]: products by x^(32 Lw 2^s)
+	for(int i = tid; i < 4 * 256 / 2; i += NT) reinterpret_cast<uint32_t *>(crc_tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.crc_tab) + i);
+	if(lw_tab)
+		for(int i = tid; i < 9 * 64 / 2; i += NT)
+			reinterpret_cast<uint32_t *>(mul_tab)[i] = __ldg(reinterpret_cast<const uint32_t *>(A.crc_tab + kCrcMulBase + (Lw >> 1) * (9 * 64)) + i);
+	// crc * x^(32 Lw 2^lev): four 16-entry lookups (a 16-step shift-and-add when Lw is outside the table)
+	auto mul_level = [&](uint32_t c, int lev) -> uint32_t {
+		if(lw_tab) {
+			const uint16_t *t = mul_tab + lev * 64;
+			return (uint32_t)t[c & 15u] ^ (uint32_t)t[16 + ((c >> 4) & 15u)] ^ (uint32_t)t[32 + ((c >> 8) & 15u)] ^ (uint32_t)t[48 + (c >> 12)];
+		}
+		return gf16_mul(c, S.mlev[lev]);
+	};
 	// level s of the combine tree multiplies by x^(32 Lw 2^s) (crc(A || B) = crc(A) x^|B| + crc(B), init 0)
 	if(tid < 9) {
-		uint32_t e = (32u * (uint32_t)Lw) << tid, m = 1;
-		for(int j = 0; e; j++, e >>= 1)
-			if(e & 1u) m = gf16_mul(m, kCrcXPow2[j % 15]);
+		uint32_t m;
+		if(Lw < 2 * kCrcLwRows) m = __ldg(&A.crc_tab[1024 + (Lw >> 1) * 9 + tid]);
+		else {
+			unsigned long long e = (32ull * (unsigned)Lw) << tid;
+			m = 1;
+			for(int j = 0; e; j++, e >>= 1)
+				if(e & 1ull) m = gf16_mul(m, kCrcXPow2[j % 15]);
+		}
 		S.mlev[tid] = m;
 	}
 	// the look-back runs here too (warp 1, or warp 0 of a one-warp CTA): its latency hides under the CRC pass
@@ -640,7 +742,7 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 #pragma unroll
 		for(int sl = 0; sl < 5; sl++) {
 			const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << sl);
-			crc = gf16_mul(crc, S.mlev[sl]) ^ other;  // meaningful in lanes that are multiples of 2 << sl; lane 0 is what counts
+			crc = mul_level(crc, sl) ^ other;  // meaningful in lanes that are multiples of 2 << sl; lane 0 is what counts
 		}
 		if(lane == 0) S.part[warp] = crc;
 	}
@@ -650,7 +752,7 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 		uint32_t crc = lane < nw ? S.part[lane] : 0;
 		for(int sl = 0; (1 << sl) < nw; sl++) {
 			const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << sl);
-			crc = gf16_mul(crc, S.mlev[5 + sl]) ^ other;
+			crc = mul_level(crc, 5 + sl) ^ other;
 		}
 		if(lane == 0) words[wend] = (words[wend] & 0xffffu) | (crc << 16);  // CRC-16, big-endian, right after the frame
 	}

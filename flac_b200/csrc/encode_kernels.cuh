@@ -82,6 +82,9 @@ __global__ void __launch_bounds__(256) k_unpack(const uint8_t *__restrict__ pack
 // s < channels: the channel; s == channels: mid; s == channels+1: side. Wasted bits are
 // shifted out here (get_wasted_bits_, stream_encoder.c:5077-5099), *after* mid/side were
 // formed from the unshifted channels (:3823-3867). flags: bit0 do_independent, bit1 do_mid_side.
+// WRITE_SIG = false is k_meta: wasted bits, subframe bps and the loose mid-side decision only -- the fast kernels
+// (k_autoc4 / k_search5 / k_emit3) read the caller's interleaved PCM themselves and never need the planar copy.
+template <bool WRITE_SIG>
 __global__ void __launch_bounds__(256) k_prep(EncK P, const int32_t *__restrict__ pcm, int32_t *__restrict__ sig,
                                              SigMeta *__restrict__ meta, int *__restrict__ blkflags)
 {
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(256) k_prep(EncK P, const int32_t *__restrict_
 		meta[(size_t)blk * nsig + tid] = m;
 	}
 	if(tid == 0) blkflags[blk] = do_indep | (do_ms << 1);
+	if(!WRITE_SIG) return;
 
 	int32_t *dst = sig + (size_t)blk * nsig * P.bs_stride;
 	if(stereo_ms) {
@@ -1044,7 +1048,7 @@ __global__ void __launch_bounds__(256) k_gather(EncK P, const uint8_t *__restric
 	const uint8_t *src = slots + (size_t)blk * P.slot_stride;
 	uint8_t *dst = out + off;
 	// head bytes up to 4-byte alignment of dst, then word copies assembled from the (aligned) slot
-	const uint32_t head = min(n, (uint32_t)((4 - (off & 3)) & 3));
+	const uint32_t head = min(n, (uint32_t)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u));  // align on the ADDRESS: `out` itself may be unaligned
 	if(tid < head) dst[tid] = src[tid];
 	const uint32_t nw = (n - head) >> 2;
 	const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);

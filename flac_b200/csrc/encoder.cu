@@ -33,11 +33,14 @@ struct Geometry {
 	int bs = 0;
 	EncK k{};
 	float *d_windows = nullptr;
+	float *d_secwin = nullptr;  // per-section weight tables over absolute sample indices (k_autoc4), stride bs + kSecwinSlack
+	bool raw_pipeline = false;  // k_meta -> k_autoc4 -> k_lpc -> k_search5 -> k_emit3: every kernel reads the caller's PCM
 	DevSection *d_secs = nullptr;
 	DevCand *d_cands = nullptr;
 	size_t search_smem = 0, emit_smem = 0;  // general kernels
-	int fast_search3 = 0;       // 0, or R_T (32/36) of the warp-per-signal search kernel (k_search4)
-	size_t search4_smem = 0;
+	int fast_search3 = 0;       // 0, or R_T (32/36) of the fast search kernel (k_search5: CTA per block, warps per signal)
+	int search_wps = 2;         // warps per signal in k_search5
+	size_t search5_smem = 0;
 	int maxord_t = 8;
 	int emit3_rt = 0;           // 0, or R_T of the resident emit kernel (k_emit3)
 	size_t emit3_smem = 0;
@@ -96,6 +99,7 @@ struct fb200_encoder {
 	uint64_t launches = 0;
 	int host_chunks = 12;   // chunks per fb200_encode_host call (FB200_HOST_CHUNKS): copy/compute overlap granularity; measured best 8-12 (tools/sweep_host_chunks.py)
 	int pipe_chunks = 1;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS); see fb200_encode_device
+	int debug_path = 0;   // FB200_DEBUG_PATH bit mask (bisecting aid): 1 = k_prep + k_autoc3 instead of k_meta + k_autoc4, 2 = general search, 4 = general emit
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
 	bool prof_on = false;
@@ -214,6 +218,21 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		FB_CUDA(cudaMemcpy(g.d_secs, secs.data(), secs.size() * sizeof(DevSection), cudaMemcpyHostToDevice));
 		FB_CUDA(cudaMalloc(&g.d_cands, cands.size() * sizeof(DevCand)));
 		FB_CUDA(cudaMemcpy(g.d_cands, cands.data(), cands.size() * sizeof(DevCand), cudaMemcpyHostToDevice));
+		// per-section weights over absolute sample indices: the window inside the section (lpc.c:68-94), zero elsewhere
+		const size_t stride = (size_t)bs + kSecwinSlack;
+		std::vector<float> sw(secs.size() * stride, 0.0f);
+		for(size_t si = 0; si < secs.size(); si++) {
+			const DevSection &S = secs[si];
+			float *dst = sw.data() + si * stride;
+			const float *w = windows.data() + S.win_off;
+			if(!S.partial) for(int i = 0; i < bs; i++) dst[i] = w[i];
+			else {
+				for(int i = 0; i < S.part_size && S.data_shift + i < bs; i++) dst[S.data_shift + i] = w[i];
+				for(int i = S.part_size; i < 2 * S.part_size && S.data_shift + i < bs; i++) dst[S.data_shift + i] = w[bs - 2 * S.part_size + i];
+			}
+		}
+		FB_CUDA(cudaMalloc(&g.d_secwin, sw.size() * sizeof(float)));
+		FB_CUDA(cudaMemcpy(g.d_secwin, sw.data(), sw.size() * sizeof(float), cudaMemcpyHostToDevice));
 	}
 	g.search_smem = (size_t)k.bs_stride * 8;
 	{
@@ -225,9 +244,12 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 			if(bs % (32 * 32) == 0) rt = 32;
 			else if(bs % (32 * 36) == 0) rt = 36;
 			const int ntl = rt ? bs / (32 * rt) : 0;  // tiles; the partition <-> lane mapping needs a power of two
-			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && 2 * search4_bytes_per_warp(bs, rt) <= 110 * 1024) {
+			const int wps = k.nsig <= 4 ? 2 : 1;
+			const size_t need = rt ? search5_smem(bs, rt, k.nsig, wps, k.max_po) : 0;
+			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && need <= 200 * 1024 && 32 * wps * k.nsig <= 256) {
 				g.fast_search3 = rt;
-				g.search4_smem = 2 * search4_bytes_per_warp(bs, rt);
+				g.search_wps = wps;
+				g.search5_smem = need;
 			}
 		}
 		// resident emit kernel: 1-2 channels, runs of R_T samples, one thread per run, at most 256 threads
@@ -235,11 +257,14 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 			const size_t need = emit3_smem_bytes(bs, g.fast_search3, k.channels, k.slot_words);
 			if(need <= 200 * 1024) { g.emit3_rt = g.fast_search3; g.emit3_smem = need; }
 		}
+		g.raw_pipeline = g.emit3_rt != 0;
 	}
 	e->geoms[bs] = g;
 	*out = &e->geoms[bs];
 	return FB200_OK;
 }
+
+static int bs_plus_slack(int bs) { return bs + kSecwinSlack; }
 
 static void use_ws(fb200_encoder *e, int b)
 {
@@ -253,11 +278,14 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	EncK k = g.k;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
-	launch_prep(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags, nb, st);
+	const bool raw = g.raw_pipeline && !e->use_v1 && e->debug_path == 0 && ((uintptr_t)d_pcm & 15) == 0;
+	if(raw) launch_meta(k, d_pcm, e->d_meta, e->d_blkflags, nb, st);  // no planar copy: the fast kernels read the caller's PCM
+	else launch_prep(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags, nb, st);
 	prof_mark(e, FB200_PROF_PREP, st);
 	e->launches++;
 	if(k.nwin > 0) {
-		if(e->use_v1) launch_autoc_general(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
+		if(raw) launch_autoc4(k, d_pcm, e->d_meta, g.d_secwin, bs_plus_slack(k.bs), g.d_secs, e->d_autoc, nitems, st);
+		else if(e->use_v1) launch_autoc_general(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		else launch_autoc3(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		prof_mark(e, FB200_PROF_AUTOC, st);
 		launch_lpc(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems, st);
@@ -279,10 +307,10 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	k.file_blocks = (int)e->file_blocks;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
-	if(g.fast_search3 && !e->use_v1) launch_search4(k, g.fast_search3, g.maxord_t, g.search4_smem, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems, st);
+	if(g.fast_search3 && !e->use_v1 && !(e->debug_path & 2)) launch_search5(k, g.fast_search3, g.maxord_t, g.search_wps, g.search5_smem, d_pcm, e->d_meta, e->d_cdesc, e->d_plans, nb, st);
 	else launch_search_general(k, g.search_smem, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems, st);
 	prof_mark(e, FB200_PROF_SEARCH, st);
-	if(g.emit3_rt && !e->use_v1 && ((uintptr_t)d_pcm & 15) == 0) {
+	if(g.emit3_rt && !e->use_v1 && !(e->debug_path & 4) && ((uintptr_t)d_pcm & 15) == 0) {
 		if((++e->epoch & kLbEpochMask) == 0) {
 			FB_CUDA(cudaMemsetAsync(e->d_lookback, 0, (size_t)e->max_blocks * sizeof(unsigned long long), st));
 			e->epoch = 1;
@@ -554,7 +582,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	ALLOC(e->d_frame_bytes, nb * sizeof(uint32_t));
 	ALLOC(e->d_chan_assign, nb * sizeof(uint32_t));
 	ALLOC(e->d_running, 2 * sizeof(unsigned long long));
-	ALLOC(e->d_crc_tab, 4 * 256 * sizeof(uint16_t));
+	ALLOC(e->d_crc_tab, (size_t)kCrcTabEntries * sizeof(uint16_t));
 	ALLOC(e->d_lookback, nb * sizeof(unsigned long long));
 	ALLOC(e->d_ticket, sizeof(unsigned));
 	ALLOC(e->d_err, sizeof(int));
@@ -593,7 +621,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 		if(device < 64 && !inited[device]) {
 			general_kernels_init(device);
 			autoc3_init(device);
-			search4_init(device);
+			autoc4_init(device);
+			search5_init(device);
 			emit3_init(device);
 			inited[device] = true;
 		}
@@ -601,6 +630,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	{
 		const char *env = getenv("FB200_FORCE_GENERAL_KERNELS");
 		e->use_v1 = env && env[0] == '1';
+		const char *dp = getenv("FB200_DEBUG_PATH");
+		if(dp) e->debug_path = atoi(dp);
 		const char *hc = getenv("FB200_HOST_CHUNKS");
 		if(hc && atoi(hc) >= 1 && atoi(hc) <= 256) e->host_chunks = atoi(hc);
 		const char *pc = getenv("FB200_PIPE_CHUNKS");
@@ -615,7 +646,7 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	if(!e) return;
 	cudaSetDevice(e->device);
 	for(auto &kv : e->geoms) {
-		cudaFree(kv.second.d_windows); cudaFree(kv.second.d_secs); cudaFree(kv.second.d_cands);
+		cudaFree(kv.second.d_windows); cudaFree(kv.second.d_secs); cudaFree(kv.second.d_cands); cudaFree(kv.second.d_secwin);
 	}
 	for(int b = 0; b < 2; b++) {
 		cudaFree(e->ws[b].d_sig); cudaFree(e->ws[b].d_meta); cudaFree(e->ws[b].d_blkflags); cudaFree(e->ws[b].d_autoc); cudaFree(e->ws[b].d_cdesc);

@@ -102,22 +102,16 @@ struct EncK {
 	int file_blocks;     // > 0: frame numbers restart every file_blocks blocks (many-file batches: one stream per file, stream_encoder.c:3772)
 };
 
-// ---- k_search4 shared layout (search_kernel.cuh)
-struct SearchWarpShared4 {
-	unsigned long long leaf[kMaxPartitions];  // |residual| sums of the finest partitions of the candidate in flight
-	uint8_t params_all[2 * kMaxPartitions];   // heap: node n = (1 << po) + p
-	uint8_t b_params[kMaxPartitions];         // parameters of the best candidate so far
-};
-
-constexpr int kSearch4ZeroRow = 36;  // words of zeros in front of a warp's signal slice
-
-__host__ __device__ constexpr size_t search4_bytes_per_warp(int bs, int R_T)
-{
-	return ((size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4 + 15) / 16 * 16 + (sizeof(SearchWarpShared4) + 15) / 16 * 16;
-}
-
+// ---- row layout shared by k_search5 and k_emit3: a signal lives in rows of R_T samples with a 36-word stride and one
+// zero row in front (the history of row 0)
+constexpr int kSearch4ZeroRow = 36;
 
 // ---- k_emit3 (emit_kernel.cuh)
+// device table of k_emit3's CRC-16 pass (uint16 entries): 4 x 256 slicing tables, combine multipliers x^(32 Lw 2^s) for odd
+// Lw < 64 and s < 9, and their nibble-product tables
+constexpr int kCrcLwRows = 32;
+constexpr int kCrcMulBase = 1024 + kCrcLwRows * 9 + 32;
+constexpr int kCrcTabEntries = kCrcMulBase + kCrcLwRows * 9 * 64;
 constexpr unsigned kLbEpochMask = 0x3fffffu;  // decoupled look-back status word: value << 24 | epoch (22 bits) << 2 | flag
 // Per-launch arguments of k_emit3 beyond EncK.
 struct Emit3Args {
@@ -147,6 +141,7 @@ struct Emit3Shared {
 	uint32_t scan[16];           // per-warp totals of the run scan
 	uint32_t mlev[16];           // CRC combine multipliers x^(32 Lw 2^s)
 	uint32_t part[16];           // per-warp CRC partials
+	uint32_t hdr[4];             // frame header bytes (big-endian words, left aligned)
 	int blk, zero_words, pad0, pad1;
 	int warm[2][FB200_MAX_LPC_ORDER];  // the first 32 samples of each channel (warm-up samples / constant value)
 };
@@ -166,6 +161,7 @@ __host__ __device__ inline size_t emit3_smem_bytes(int bs, int R_T, int nch, int
 // ---- launchers (one translation unit per kernel family; encoder.cu holds no device code)
 // general_kernels.cu
 void launch_unpack(const void *packed, int bytes_per_sample, int32_t *pcm, unsigned long long n, int bps, int *err, cudaStream_t st);
+void launch_meta(const EncK &k, const int32_t *pcm, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
 void launch_prep(const EncK &k, const int32_t *pcm, int32_t *sig, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
 void launch_autoc_general(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
 void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, cudaStream_t st);
@@ -178,9 +174,13 @@ void general_kernels_init(int device);  // raises the dynamic shared-memory limi
 // autoc_kernel.cu
 void launch_autoc3(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
 void autoc3_init(int device);
+void launch_autoc4(const EncK &k, const int32_t *pcm, const SigMeta *meta, const float *secwin, int secwin_stride, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
+void autoc4_init(int device);
+constexpr int kSecwinSlack = 160;  // zero floats behind every per-section weight table (>= the largest autocorrelation tile)
 // search_kernel.cu
-void launch_search4(const EncK &k, int rt, int maxord_t, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st);
-void search4_init(int device);
+void launch_search5(const EncK &k, int rt, int maxord_t, int wps, size_t smem, const int32_t *pcm, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nb, cudaStream_t st);
+size_t search5_smem(int bs, int rt, int nsig, int wps, int max_po);
+void search5_init(int device);
 // emit_kernel.cu
 void launch_emit3(const EncK &k, int rt, int maxord_t, size_t smem, const Emit3Args &a, int nb, cudaStream_t st);
 void launch_crc16_tables(uint16_t *tab, cudaStream_t st);

@@ -5,7 +5,12 @@ namespace fb200 {
 
 void launch_prep(const EncK &k, const int32_t *pcm, int32_t *sig, SigMeta *meta, int *blkflags, int nb, cudaStream_t st)
 {
-	k_prep<<<nb, 256, 0, st>>>(k, pcm, sig, meta, blkflags);
+	k_prep<true><<<nb, 256, 0, st>>>(k, pcm, sig, meta, blkflags);
+}
+
+void launch_meta(const EncK &k, const int32_t *pcm, SigMeta *meta, int *blkflags, int nb, cudaStream_t st)
+{
+	k_prep<false><<<nb, 256, 0, st>>>(k, pcm, nullptr, meta, blkflags);
 }
 
 void launch_unpack(const void *packed, int bytes_per_sample, int32_t *pcm, unsigned long long n, int bps, int *err, cudaStream_t st)

@@ -1,44 +1,52 @@
-// search_kernel.cu -- k_search4 and its launcher.
+// search_kernel.cu -- k_search5 and its launcher.
 #include "search_kernel.cuh"
 
 namespace fb200 {
 
-template <int MO>
-static void search4(const EncK &k, int rt, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st)
+template <int MO, int WPS>
+static void search5(const EncK &k, int rt, size_t smem, const int32_t *pcm, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nb, cudaStream_t st)
 {
-	const int grid = (nitems + 1) / 2;
+	const int nt = 32 * WPS * k.nsig;
 	const bool widek = k.bps > 16;
 	if(rt == 32) {
-		if(widek) k_search4<32, MO, 2, true><<<grid, 64, smem, st>>>(k, sig, meta, cdesc, plans, nitems);
-		else k_search4<32, MO, 2, false><<<grid, 64, smem, st>>>(k, sig, meta, cdesc, plans, nitems);
+		if(widek) k_search5<32, MO, WPS, true><<<nb, nt, smem, st>>>(k, pcm, meta, cdesc, plans);
+		else k_search5<32, MO, WPS, false><<<nb, nt, smem, st>>>(k, pcm, meta, cdesc, plans);
 	}
 	else {
-		if(widek) k_search4<36, MO, 2, true><<<grid, 64, smem, st>>>(k, sig, meta, cdesc, plans, nitems);
-		else k_search4<36, MO, 2, false><<<grid, 64, smem, st>>>(k, sig, meta, cdesc, plans, nitems);
+		if(widek) k_search5<36, MO, WPS, true><<<nb, nt, smem, st>>>(k, pcm, meta, cdesc, plans);
+		else k_search5<36, MO, WPS, false><<<nb, nt, smem, st>>>(k, pcm, meta, cdesc, plans);
 	}
 }
 
-void launch_search4(const EncK &k, int rt, int maxord_t, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st)
+void launch_search5(const EncK &k, int rt, int maxord_t, int wps, size_t smem, const int32_t *pcm, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nb, cudaStream_t st)
 {
-	if(maxord_t == 8) search4<8>(k, rt, smem, sig, meta, cdesc, plans, nitems, st);
-	else if(maxord_t == 12) search4<12>(k, rt, smem, sig, meta, cdesc, plans, nitems, st);
-	else search4<32>(k, rt, smem, sig, meta, cdesc, plans, nitems, st);
+	if(wps == 2) {
+		if(maxord_t == 8) search5<8, 2>(k, rt, smem, pcm, meta, cdesc, plans, nb, st);
+		else if(maxord_t == 12) search5<12, 2>(k, rt, smem, pcm, meta, cdesc, plans, nb, st);
+		else search5<32, 2>(k, rt, smem, pcm, meta, cdesc, plans, nb, st);
+	}
+	else {
+		if(maxord_t == 8) search5<8, 1>(k, rt, smem, pcm, meta, cdesc, plans, nb, st);
+		else if(maxord_t == 12) search5<12, 1>(k, rt, smem, pcm, meta, cdesc, plans, nb, st);
+		else search5<32, 1>(k, rt, smem, pcm, meta, cdesc, plans, nb, st);
+	}
 }
 
-template <int MO>
-static void search4_attrs()
+size_t search5_smem(int bs, int rt, int nsig, int wps, int max_po) { return search5_smem_bytes(bs, rt, nsig, wps, max_po); }
+
+template <int MO, int WPS>
+static void search5_attrs()
 {
-	cudaFuncSetAttribute(k_search4<32, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search4<36, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search4<32, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-	cudaFuncSetAttribute(k_search4<36, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+	cudaFuncSetAttribute(k_search5<32, MO, WPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_search5<36, MO, WPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_search5<32, MO, WPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_search5<36, MO, WPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-void search4_init(int)
+void search5_init(int)
 {
-	search4_attrs<8>();
-	search4_attrs<12>();
-	search4_attrs<32>();
+	search5_attrs<8, 1>(); search5_attrs<12, 1>(); search5_attrs<32, 1>();
+	search5_attrs<8, 2>(); search5_attrs<12, 2>(); search5_attrs<32, 2>();
 }
 
 }  // namespace fb200

@@ -225,6 +225,46 @@ const char *const FLAC__StreamEncoderInitStatusString[] = {
 	"FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_QLP_COEFF_PRECISION", "FLAC__STREAM_ENCODER_INIT_STATUS_BLOCK_SIZE_TOO_SMALL_FOR_LPC_ORDER",
 	"FLAC__STREAM_ENCODER_INIT_STATUS_NOT_STREAMABLE", "FLAC__STREAM_ENCODER_INIT_STATUS_INVALID_METADATA",
 	"FLAC__STREAM_ENCODER_INIT_STATUS_ALREADY_INITIALIZED"};
+// The enumerator names of the remaining status enums, in enum order (include/FLAC/stream_encoder.h:388-454,
+// include/FLAC/stream_decoder.h:297-480, include/FLAC/format.h). Clients index them directly: src/flac/decode.c:1834,
+// src/flac/encode.c:2677, examples/c/decode/file/main.c.
+#define FB_S(x) #x
+const char *const FLAC__StreamEncoderReadStatusString[] = {
+	FB_S(FLAC__STREAM_ENCODER_READ_STATUS_CONTINUE), FB_S(FLAC__STREAM_ENCODER_READ_STATUS_END_OF_STREAM), FB_S(FLAC__STREAM_ENCODER_READ_STATUS_ABORT),
+	FB_S(FLAC__STREAM_ENCODER_READ_STATUS_UNSUPPORTED)};
+const char *const FLAC__StreamEncoderWriteStatusString[] = {FB_S(FLAC__STREAM_ENCODER_WRITE_STATUS_OK), FB_S(FLAC__STREAM_ENCODER_WRITE_STATUS_FATAL_ERROR)};
+const char *const FLAC__StreamEncoderSeekStatusString[] = {
+	FB_S(FLAC__STREAM_ENCODER_SEEK_STATUS_OK), FB_S(FLAC__STREAM_ENCODER_SEEK_STATUS_ERROR), FB_S(FLAC__STREAM_ENCODER_SEEK_STATUS_UNSUPPORTED)};
+const char *const FLAC__StreamEncoderTellStatusString[] = {
+	FB_S(FLAC__STREAM_ENCODER_TELL_STATUS_OK), FB_S(FLAC__STREAM_ENCODER_TELL_STATUS_ERROR), FB_S(FLAC__STREAM_ENCODER_TELL_STATUS_UNSUPPORTED)};
+const char *const FLAC__StreamDecoderInitStatusString[] = {
+	FB_S(FLAC__STREAM_DECODER_INIT_STATUS_OK), FB_S(FLAC__STREAM_DECODER_INIT_STATUS_UNSUPPORTED_CONTAINER), FB_S(FLAC__STREAM_DECODER_INIT_STATUS_INVALID_CALLBACKS),
+	FB_S(FLAC__STREAM_DECODER_INIT_STATUS_MEMORY_ALLOCATION_ERROR), FB_S(FLAC__STREAM_DECODER_INIT_STATUS_ERROR_OPENING_FILE),
+	FB_S(FLAC__STREAM_DECODER_INIT_STATUS_ALREADY_INITIALIZED)};
+const char *const FLAC__StreamDecoderReadStatusString[] = {
+	FB_S(FLAC__STREAM_DECODER_READ_STATUS_CONTINUE), FB_S(FLAC__STREAM_DECODER_READ_STATUS_END_OF_STREAM), FB_S(FLAC__STREAM_DECODER_READ_STATUS_ABORT),
+	FB_S(FLAC__STREAM_DECODER_READ_STATUS_END_OF_LINK)};
+const char *const FLAC__StreamDecoderSeekStatusString[] = {
+	FB_S(FLAC__STREAM_DECODER_SEEK_STATUS_OK), FB_S(FLAC__STREAM_DECODER_SEEK_STATUS_ERROR), FB_S(FLAC__STREAM_DECODER_SEEK_STATUS_UNSUPPORTED)};
+const char *const FLAC__StreamDecoderTellStatusString[] = {
+	FB_S(FLAC__STREAM_DECODER_TELL_STATUS_OK), FB_S(FLAC__STREAM_DECODER_TELL_STATUS_ERROR), FB_S(FLAC__STREAM_DECODER_TELL_STATUS_UNSUPPORTED)};
+const char *const FLAC__StreamDecoderLengthStatusString[] = {
+	FB_S(FLAC__STREAM_DECODER_LENGTH_STATUS_OK), FB_S(FLAC__STREAM_DECODER_LENGTH_STATUS_ERROR), FB_S(FLAC__STREAM_DECODER_LENGTH_STATUS_UNSUPPORTED)};
+const char *const FLAC__StreamDecoderWriteStatusString[] = {FB_S(FLAC__STREAM_DECODER_WRITE_STATUS_CONTINUE), FB_S(FLAC__STREAM_DECODER_WRITE_STATUS_ABORT)};
+const char *const FLAC__StreamDecoderErrorStatusString[] = {
+	FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_LOST_SYNC), FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_BAD_HEADER), FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_FRAME_CRC_MISMATCH),
+	FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_UNPARSEABLE_STREAM), FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_BAD_METADATA),
+	FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_OUT_OF_BOUNDS), FB_S(FLAC__STREAM_DECODER_ERROR_STATUS_MISSING_FRAME)};
+// format.h tables: short names, as the analysis output of `flac -a` prints them (src/flac/analyze.c)
+const char *const FLAC__EntropyCodingMethodTypeString[] = {"PARTITIONED_RICE", "PARTITIONED_RICE2"};
+const char *const FLAC__SubframeTypeString[] = {"CONSTANT", "VERBATIM", "FIXED", "LPC"};
+const char *const FLAC__ChannelAssignmentString[] = {"INDEPENDENT", "LEFT_SIDE", "RIGHT_SIDE", "MID_SIDE"};
+const char *const FLAC__FrameNumberTypeString[] = {"FRAME_NUMBER_TYPE_FRAME_NUMBER", "FRAME_NUMBER_TYPE_SAMPLE_NUMBER"};
+const char *const FLAC__MetadataTypeString[] = {"STREAMINFO", "PADDING", "APPLICATION", "SEEKTABLE", "VORBIS_COMMENT", "CUESHEET", "PICTURE"};
+#undef FB_S
+// built without libogg, like the oracle configuration (include/FLAC/export.h:107, stream_decoder.c:59)
+int FLAC_API_SUPPORTS_OGG_FLAC = 0;
+
 const char *const FLAC__StreamDecoderStateString[] = {
 	"FLAC__STREAM_DECODER_SEARCH_FOR_METADATA", "FLAC__STREAM_DECODER_READ_METADATA", "FLAC__STREAM_DECODER_SEARCH_FOR_FRAME_SYNC",
 	"FLAC__STREAM_DECODER_READ_FRAME", "FLAC__STREAM_DECODER_END_OF_STREAM", "FLAC__STREAM_DECODER_OGG_ERROR", "FLAC__STREAM_DECODER_SEEK_ERROR",
@@ -408,6 +448,12 @@ FLAC__bool FLAC__stream_encoder_set_metadata(FLAC__StreamEncoder *e, FLAC__Strea
 
 FLAC__bool FLAC__stream_encoder_get_do_md5(const FLAC__StreamEncoder *e) { return e->protected_->do_md5; }
 FLAC__StreamEncoderState FLAC__stream_encoder_get_state(const FLAC__StreamEncoder *e) { return e->protected_->state; }
+// the verify decoder is the batch decoder of the same library: its failures surface as encoder states (stream_encoder.h:1311);
+// as a decoder object it is always searching for the next frame
+FLAC__StreamDecoderState FLAC__stream_encoder_get_verify_decoder_state(const FLAC__StreamEncoder *e)
+{
+	return e->protected_->verify ? FLAC__STREAM_DECODER_SEARCH_FOR_FRAME_SYNC : FLAC__STREAM_DECODER_UNINITIALIZED;
+}
 const char *FLAC__stream_encoder_get_resolved_state_string(const FLAC__StreamEncoder *e) { return FLAC__StreamEncoderStateString[e->protected_->state]; }
 void FLAC__stream_encoder_get_verify_decoder_error_stats(const FLAC__StreamEncoder *e, FLAC__uint64 *absolute_sample, uint32_t *frame_number, uint32_t *channel, uint32_t *sample, FLAC__int32 *expected, FLAC__int32 *got)
 {
@@ -805,9 +851,11 @@ struct FLAC__StreamDecoderPrivate {
 	bool respond[128];
 	std::vector<uint8_t> in;     // everything read so far that was not consumed
 	size_t in_pos;
+	uint64_t consumed_before_in;  // bytes dropped from the front of `in` so far
 	bool eof, metadata_done, indexed, has_streaminfo, did_seek;
 	FLAC__StreamMetadata_StreamInfo si;
 	std::vector<uint8_t> audio;  // all frame bytes (+ slack)
+	uint64_t audio_offset;       // stream byte offset of audio[0] (for get_decode_position)
 	std::vector<FrameIndexEntry> index;
 	std::vector<uint64_t> first_sample;  // per frame
 	size_t next_frame;
@@ -1068,6 +1116,7 @@ static bool dec_prepare_audio(FLAC__StreamDecoder *d)
 	while(!q->eof) {
 		if(!dec_fill(d, (q->in.size() - q->in_pos) + (4 << 20)) && d->protected_->state == FLAC__STREAM_DECODER_ABORTED) return false;
 	}
+	q->audio_offset = q->consumed_before_in + q->in_pos;
 	q->audio.assign(q->in.begin() + (long)q->in_pos, q->in.end());
 	q->audio.resize(q->audio.size() + 64, 0);
 	q->in.clear(); q->in.shrink_to_fit(); q->in_pos = 0;
@@ -1216,13 +1265,40 @@ FLAC__ChannelAssignment FLAC__stream_decoder_get_channel_assignment(const FLAC__
 uint32_t FLAC__stream_decoder_get_bits_per_sample(const FLAC__StreamDecoder *d) { return d->protected_->bits_per_sample; }
 uint32_t FLAC__stream_decoder_get_sample_rate(const FLAC__StreamDecoder *d) { return d->protected_->sample_rate; }
 uint32_t FLAC__stream_decoder_get_blocksize(const FLAC__StreamDecoder *d) { return d->protected_->blocksize; }
-FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder *, FLAC__uint64 *) { return false; /* the whole stream is read ahead; no meaningful byte position */ }
+FLAC__bool FLAC__stream_decoder_get_decode_position(const FLAC__StreamDecoder *d, FLAC__uint64 *position)
+{
+	// byte offset (from the start of the stream) of the next frame to be delivered -- what the reference's tell callback minus
+	// its unconsumed input gives (stream_decoder.c:1087-1110); undefined (false) before the audio has been indexed
+	const FLAC__StreamDecoderPrivate *q = d->private_;
+	if(!position || !q->indexed) return false;
+	const uint64_t audio_bytes = q->audio.size() >= 64 ? q->audio.size() - 64 : 0;
+	*position = q->audio_offset + (q->next_frame < q->index.size() ? q->index[q->next_frame].offset : audio_bytes);
+	return true;
+}
+// native FLAC has exactly one link; the chained-stream calls of API 14 (stream_decoder.h:970, 1022, 1150, 1538, 1664, 1754)
+// reduce to their single-link meaning, as in the reference when the stream is not Ogg
+FLAC__bool FLAC__stream_decoder_get_decode_chained_stream(const FLAC__StreamDecoder *) { return false; }
+FLAC__uint64 FLAC__stream_decoder_find_total_samples(FLAC__StreamDecoder *d)
+{
+	// stream_decoder.c: native FLAC returns STREAMINFO's total when known; 0 = unknown
+	return d->private_->has_streaminfo ? d->private_->si.total_samples : 0;
+}
+int32_t FLAC__stream_decoder_get_link_lengths(FLAC__StreamDecoder *, FLAC__uint64 **link_lengths)
+{
+	if(link_lengths) *link_lengths = nullptr;
+	return -1;  // FLAC__STREAM_DECODER_GET_LINK_LENGTHS_INVALID: not an Ogg chain
+}
+uint32_t FLAC__stream_decoder_get_input_bytes_unconsumed(const FLAC__StreamDecoder *d)
+{
+	const FLAC__StreamDecoderPrivate *q = d->private_;
+	return (uint32_t)std::min<size_t>(q->in.size() - q->in_pos, 0xffffffffu);
+}
 const void *FLAC__stream_decoder_get_client_data(FLAC__StreamDecoder *d) { return d->private_->client_data; }
 
 static FLAC__StreamDecoderInitStatus dec_init_common(FLAC__StreamDecoder *d)
 {
 	FLAC__StreamDecoderPrivate *q = d->private_;
-	q->in.clear(); q->in_pos = 0; q->eof = false; q->metadata_done = false; q->indexed = false; q->has_streaminfo = false; q->did_seek = false;
+	q->in.clear(); q->in_pos = 0; q->consumed_before_in = 0; q->audio_offset = 0; q->eof = false; q->metadata_done = false; q->indexed = false; q->has_streaminfo = false; q->did_seek = false;
 	q->next_frame = 0; q->skip_samples = 0; q->batch_first = q->batch_count = 0; q->samples_decoded = 0;
 	memset(&q->si, 0, sizeof q->si);
 	d->protected_->state = FLAC__STREAM_DECODER_SEARCH_FOR_METADATA;
@@ -1335,6 +1411,25 @@ FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder 
 	if(!dec_prepare_audio(d)) return false;
 	while(d->protected_->state != FLAC__STREAM_DECODER_END_OF_STREAM)
 		if(!dec_deliver_next(d)) return false;
+	return true;
+}
+
+FLAC__bool FLAC__stream_decoder_finish_link(FLAC__StreamDecoder *d)
+{
+	// only meaningful in END_OF_LINK state, which native FLAC never enters (stream_decoder.h:1538)
+	return !DEC_UNINIT(d) && d->protected_->state == FLAC__STREAM_DECODER_END_OF_LINK;
+}
+FLAC__bool FLAC__stream_decoder_process_until_end_of_link(FLAC__StreamDecoder *d) { return FLAC__stream_decoder_process_until_end_of_stream(d); }
+FLAC__bool FLAC__stream_decoder_skip_single_link(FLAC__StreamDecoder *d)
+{
+	// one link == the whole stream: skip to its end without decoding
+	if(DEC_UNINIT(d)) return false;
+	FLAC__StreamDecoderPrivate *q = d->private_;
+	if(!q->metadata_done && !dec_read_metadata(d)) return d->protected_->state == FLAC__STREAM_DECODER_END_OF_STREAM;
+	if(!dec_prepare_audio(d)) return false;
+	q->next_frame = q->index.size();
+	q->did_seek = true;
+	d->protected_->state = FLAC__STREAM_DECODER_END_OF_STREAM;
 	return true;
 }
 

@@ -201,7 +201,7 @@ int fb200_decode_device(fb200_decoder *dec, const uint8_t *d_frames, const uint6
 
 uint64_t fb200_decoder_launch_count(const fb200_decoder *dec);
 
-enum { FB200_DPROF_PARSE = 0, FB200_DPROF_CRC, FB200_DPROF_MERGE, FB200_DPROF_KERNELS };
+enum { FB200_DPROF_WALK = 0, FB200_DPROF_CRC, FB200_DPROF_FRAMES, FB200_DPROF_KERNELS };  /* k_dec_walk, k_dec_crc, k_dec_frames */
 int fb200_decoder_set_profiling(fb200_decoder *dec, int on);
 int fb200_decoder_get_profile(fb200_decoder *dec, double ms[FB200_DPROF_KERNELS], uint64_t launches[FB200_DPROF_KERNELS], int reset);
 

@@ -323,6 +323,38 @@ FLAC__bool FLAC__stream_decoder_process_until_end_of_metadata(FLAC__StreamDecode
 FLAC__bool FLAC__stream_decoder_process_until_end_of_stream(FLAC__StreamDecoder *decoder);
 FLAC__bool FLAC__stream_decoder_skip_single_frame(FLAC__StreamDecoder *decoder);
 FLAC__bool FLAC__stream_decoder_seek_absolute(FLAC__StreamDecoder *decoder, FLAC__uint64 sample);
+/* API 14 additions for chained (Ogg) streams, include/FLAC/stream_decoder.h:970, 1022, 1150, 1538, 1664, 1754: native FLAC is
+ * one link, so these reduce to their single-link meaning. */
+FLAC__bool FLAC__stream_decoder_get_decode_chained_stream(const FLAC__StreamDecoder *decoder);
+FLAC__uint64 FLAC__stream_decoder_find_total_samples(FLAC__StreamDecoder *decoder);
+int32_t FLAC__stream_decoder_get_link_lengths(FLAC__StreamDecoder *decoder, FLAC__uint64 **link_lengths);
+FLAC__bool FLAC__stream_decoder_finish_link(FLAC__StreamDecoder *decoder);
+FLAC__bool FLAC__stream_decoder_process_until_end_of_link(FLAC__StreamDecoder *decoder);
+FLAC__bool FLAC__stream_decoder_skip_single_link(FLAC__StreamDecoder *decoder);
+/* private export used by the reference's own tools (src/libFLAC/include/protected/stream_decoder.h) */
+uint32_t FLAC__stream_decoder_get_input_bytes_unconsumed(const FLAC__StreamDecoder *decoder);
+/* include/FLAC/stream_encoder.h:1311 (declared here because it returns a decoder state) */
+FLAC__StreamDecoderState FLAC__stream_encoder_get_verify_decoder_state(const FLAC__StreamEncoder *encoder);
+
+/* Enumerator-name tables, indexable by the enum value (include/FLAC/stream_encoder.h:388-454, stream_decoder.h:297-480,
+ * format.h); FLAC_API_SUPPORTS_OGG_FLAC == 0: built without libogg (include/FLAC/export.h:107). */
+extern const char *const FLAC__StreamEncoderReadStatusString[];
+extern const char *const FLAC__StreamEncoderWriteStatusString[];
+extern const char *const FLAC__StreamEncoderSeekStatusString[];
+extern const char *const FLAC__StreamEncoderTellStatusString[];
+extern const char *const FLAC__StreamDecoderInitStatusString[];
+extern const char *const FLAC__StreamDecoderReadStatusString[];
+extern const char *const FLAC__StreamDecoderSeekStatusString[];
+extern const char *const FLAC__StreamDecoderTellStatusString[];
+extern const char *const FLAC__StreamDecoderLengthStatusString[];
+extern const char *const FLAC__StreamDecoderWriteStatusString[];
+extern const char *const FLAC__StreamDecoderErrorStatusString[];
+extern const char *const FLAC__EntropyCodingMethodTypeString[];
+extern const char *const FLAC__SubframeTypeString[];
+extern const char *const FLAC__ChannelAssignmentString[];
+extern const char *const FLAC__FrameNumberTypeString[];
+extern const char *const FLAC__MetadataTypeString[];
+extern int FLAC_API_SUPPORTS_OGG_FLAC;
 
 #ifdef __cplusplus
 }
