@@ -59,6 +59,13 @@ class SubframePlan(C.Structure):
     ]
 
 
+class SubframeInfo(C.Structure):
+    """Mirror of fb200_subframe_info (what FLAC__Frame.subframes[] carries)."""
+    _fields_ = [("type", C.c_uint8), ("order", C.c_uint8), ("wasted_bits", C.c_uint8), ("qlp_coeff_precision", C.c_uint8),
+                ("quantization_level", C.c_int8), ("entropy_method", C.c_uint8), ("partition_order", C.c_uint8), ("reserved", C.c_uint8),
+                ("qlp_coeff", C.c_int32 * MAX_LPC_ORDER), ("warmup", C.c_int32 * MAX_LPC_ORDER)]
+
+
 _lib = None
 
 
@@ -114,6 +121,16 @@ def lib():
         L.fb200_decode_device.restype = C.c_int
         L.fb200_decode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                           C.c_void_p, C.c_int]
+        L.fb200_decoder_get_frame_status.restype = C.c_int
+        L.fb200_decoder_get_frame_status.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.fb200_decoder_enable_subframe_info.restype = C.c_int
+        L.fb200_decoder_enable_subframe_info.argtypes = [C.c_void_p, C.c_int]
+        L.fb200_decoder_get_subframe_info.restype = C.c_int
+        L.fb200_decoder_get_subframe_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.fb200_decoder_index_host.restype = C.c_int
+        L.fb200_decoder_index_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.fb200_decode_indexed_host.restype = C.c_int
+        L.fb200_decode_indexed_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.fb200_decoder_launch_count.restype = C.c_uint64
         L.fb200_decoder_launch_count.argtypes = [C.c_void_p]
         L.fb200_decoder_set_profiling.restype = C.c_int
@@ -301,6 +318,42 @@ class Decoder:
             raise FlacB200Error(-5, f"{bad.value} frames failed to decode")
         n = ns.value if total_samples is None else total_samples
         return out[:n]
+
+    def frame_status(self, nframes):
+        """Per-frame status words of the last host decode: low byte 0 = ok, upper 24 bits = blocksize."""
+        st = np.zeros(nframes, dtype=np.uint32)
+        _check(lib().fb200_decoder_get_frame_status(self._h, st.ctypes.data, nframes))
+        return st
+
+    def enable_subframe_info(self, on=True):
+        _check(lib().fb200_decoder_enable_subframe_info(self._h, 1 if on else 0))
+
+    def subframe_info(self, nframes):
+        """[(frame, channel)] SubframeInfo records of the last decode call (after enable_subframe_info)."""
+        info = (SubframeInfo * (nframes * self.cfg.channels))()
+        _check(lib().fb200_decoder_get_subframe_info(self._h, info, nframes))
+        return info
+
+    def index(self, stream, capacity=1 << 20):
+        """GPU front end: ascending byte offsets of every sync code + self-consistent frame header in `stream`
+        (which stays resident on the device for decode_indexed)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        cand = np.zeros(capacity, dtype=np.uint64)
+        n = C.c_uint32(0)
+        _check(lib().fb200_decoder_index_host(self._h, stream.ctypes.data, stream.size, cand.ctypes.data, capacity, C.byref(n)))
+        self._indexed_bytes = stream.size
+        return cand[:n.value].copy()
+
+    def decode_indexed(self, begins, max_frame_bytes):
+        """Decode the frames starting at `begins` of the indexed stream. Returns (pcm [n*blocksize, ch], status, frame_bytes)."""
+        begins = np.ascontiguousarray(begins, dtype=np.uint64)
+        n = begins.size
+        out = np.zeros((n * self.cfg.blocksize, self.cfg.channels), dtype=np.int32)
+        st = np.zeros(n, dtype=np.uint32)
+        fb = np.zeros(n, dtype=np.uint32)
+        _check(lib().fb200_decode_indexed_host(self._h, begins.ctypes.data, n, max_frame_bytes, self._indexed_bytes, out.ctypes.data,
+                                               n * self.cfg.blocksize, st.ctypes.data, fb.ctypes.data))
+        return out, st, fb
 
     def decode_device(self, d_frames_ptr, d_offsets_ptr, nframes, d_pcm_ptr, pcm_capacity_samples, d_status_ptr, stream=0, sync=False):
         _check(lib().fb200_decode_device(self._h, d_frames_ptr, d_offsets_ptr, nframes, d_pcm_ptr, pcm_capacity_samples, d_status_ptr,

@@ -186,7 +186,11 @@ __global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict
 	const int sec = blockIdx.x / groups;
 	const int item0 = (blockIdx.x - sec * groups) << 5;
 	const int item = min(item0 + lane, nitems - 1);
-	const SigMeta M = meta[item];
+	// meta == nullptr: the wasted-bits shift is left to k_lpc (the windowed products and their sums scale EXACTLY by powers of
+	// two, so autoc(x >> w) == autoc(x) * 2^-2w bit for bit) and every signal is analysed -- k_meta then runs concurrently
+	SigMeta M;
+	M.wasted = 0; M.bps = 1;
+	if(meta) M = meta[item];
 	const bool live = item0 + lane < nitems && M.bps != 0;
 	if(!__any_sync(0xffffffffu, live)) return;
 

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fb200_internal.h"
 
 namespace fb200 {
@@ -63,31 +65,69 @@ struct DecSubframeInfo {
 	int32_t warmup[FB200_MAX_LPC_ORDER];  // warm-up samples (constant: [0] = the value)
 };
 
-// MSB-first bit reader over global memory: 64-bit left-aligned accumulator, at least 32 valid bits after every refill,
-// zeros past word `nwords`.
+// MSB-first bit reader over global memory: a 64-bit left-aligned accumulator (at least 32 valid bits after every refill) and
+// ONE word of look-ahead in a register. A lane walks its own frame, so nothing but the reader itself can hide its load
+// latency: the word that enters the accumulator was loaded one refill earlier (covers the L1 latency), and whenever the
+// reader enters a new 128-byte line it prefetches the line two ahead into L1 (covers L2 / DRAM). The refill is branch-free
+// (predicated), so lanes at different bit positions stay converged. Words past `nwords` read as zeros: no read leaves the
+// frame's last 16-byte granule. (First version: one dependent 32-bit load per refill = ~250 cycles per Rice code; second: a
+// three-deep queue of 128-bit loads whose clamping touched the data at once and whose rotation cost 5 moves per word.)
 struct BitRd {
-	const uint32_t *words;
-	uint32_t nwords, widx, pos, end;
+	const uint32_t *words;         // 4-byte aligned address at or below the frame's first byte
+	uint32_t nwords;               // words (from `words`) that may be read
+	uint32_t widx;                 // index of the next word to LOAD (nextw holds word widx - 1)
+	uint32_t pos, end;             // bit position / end of the frame, relative to `words`
+	uint32_t nextw;                // look-ahead word, already byte-swapped
 	unsigned long long acc;
 	int nbits;
-	__device__ __forceinline__ uint32_t load(uint32_t i) const { return i < nwords ? __byte_perm(__ldg(words + i), 0, 0x0123) : 0u; }
+	__device__ __forceinline__ uint32_t load(uint32_t i) const
+	{
+		uint32_t v = 0u;
+		if(i < nwords) v = __ldg(words + i);
+		return __byte_perm(v, 0, 0x0123);
+	}
+	__device__ __forceinline__ void prefetch_ahead(uint32_t i) const
+	{
+		// i = index of a word in a new 128-byte line (relative to an aligned `words`, lines start at multiples of 32 words)
+		if(i + 64u < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + i + 64u));
+	}
+	__device__ __forceinline__ void refill()
+	{
+		const bool need = nbits <= 32;
+		const unsigned long long add = (unsigned long long)nextw << ((32 - nbits) & 63);
+		acc |= need ? add : 0ull;
+		nbits += need ? 32 : 0;
+		if(need) {
+			nextw = load(widx);
+			if((widx & 31u) == 0u) prefetch_ahead(widx);
+			widx++;
+		}
+	}
+	__device__ __forceinline__ void reseat()  // (re)build the accumulator at bit position `pos`
+	{
+		widx = pos >> 5;
+		const uint32_t hi = load(widx), lo = load(widx + 1u);
+		nextw = load(widx + 2u);
+		prefetch_ahead(widx & ~31u);
+		if(((widx & ~31u) + 32u) < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (widx & ~31u) + 32u));
+		widx += 3u;
+		acc = ((unsigned long long)hi << 32) | lo;
+		nbits = 64;
+		const uint32_t r = pos & 31u;
+		acc <<= r;
+		nbits -= (int)r;
+		refill();
+	}
 	// p: first byte of the frame, len: frame bytes, bit: bit offset inside the frame to start at
 	__device__ __forceinline__ void init(const uint8_t *p, uint32_t len, uint32_t bit)
 	{
 		const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-		words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-		const uint32_t lead = (uint32_t)(a & 3) * 8;
-		nwords = (lead + len * 8 + 31) >> 5;
+		words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)127);  // line aligned: prefetch decisions are on widx % 32
+		const uint32_t lead = (uint32_t)(a & 127) * 8;
+		nwords = len ? (lead + len * 8 + 31) >> 5 : 0u;
 		end = lead + len * 8;
 		pos = lead + bit;
 		reseat();
-	}
-	__device__ __forceinline__ void refill()
-	{
-		if(nbits <= 32) {
-			acc |= (unsigned long long)load(widx++) << (32 - nbits);
-			nbits += 32;
-		}
 	}
 	__device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(acc >> 32); }
 	__device__ __forceinline__ void consume(uint32_t n)  // 0..32
@@ -108,17 +148,6 @@ struct BitRd {
 		const int32_t v = (int32_t)peek32() >> (32 - n);
 		consume(n);
 		return v;
-	}
-	__device__ __forceinline__ void reseat()  // after pos was moved arbitrarily
-	{
-		widx = pos >> 5;
-		acc = ((unsigned long long)load(widx) << 32) | load(widx + 1);
-		widx += 2;
-		nbits = 64;
-		const uint32_t r = pos & 31u;
-		acc <<= r;
-		nbits -= (int)r;
-		refill();
 	}
 	__device__ __forceinline__ void skip(uint32_t n)  // any number of bits
 	{
@@ -182,14 +211,57 @@ __device__ __forceinline__ SubHdr read_sub_header(BitRd &br, uint32_t bps)
 	return h;
 }
 
+// ================================================================ k_dec_scan
+// The decoder front end (frame_sync_ + read_frame_header_, stream_decoder.c:2321-2371, 2624-2947) for a whole stream at
+// once: every byte position is tested for sync code + a self-consistent header (reserved bits, code points, UTF-8 number,
+// CRC-8). Candidates are appended unordered (the host sorts the short list); false positives (~2^-25 per byte) are weeded
+// out later by decoding: a candidate that does not parse / fails its CRC-16, or lies inside an accepted frame, is dropped.
+__global__ void __launch_bounds__(256) k_dec_scan(const uint8_t *__restrict__ data, unsigned long long n, unsigned long long *__restrict__ cand,
+                                                 unsigned cap, unsigned *__restrict__ count)
+{
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	for(unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p + 6 <= n; p += stride) {
+		if(data[p] != 0xFF || (data[p + 1] & 0xFE) != 0xF8) continue;
+		const uint8_t *h = data + p;
+		const unsigned long long avail = n - p;
+		const uint32_t variable = h[1] & 1, bs_code = h[2] >> 4, sr_code = h[2] & 15, ca_code = h[3] >> 4, bps_code = (h[3] >> 1) & 7;
+		if((h[3] & 1) || bs_code == 0 || sr_code == 15 || ca_code > 10 || bps_code == 3) continue;
+		uint32_t pos = 4;
+		const uint32_t first = h[pos++];
+		int nb;
+		if(!(first & 0x80)) nb = 0;
+		else if((first & 0xE0) == 0xC0) nb = 1;
+		else if((first & 0xF0) == 0xE0) nb = 2;
+		else if((first & 0xF8) == 0xF0) nb = 3;
+		else if((first & 0xFC) == 0xF8) nb = 4;
+		else if((first & 0xFE) == 0xFC) nb = 5;
+		else if(first == 0xFE && variable) nb = 6;
+		else continue;
+		const uint32_t hl = pos + nb + (bs_code == 6 ? 1 : bs_code == 7 ? 2 : 0) + (sr_code == 12 ? 1 : sr_code >= 13 ? 2 : 0);
+		if(hl + 1 > avail) continue;
+		bool ok = true;
+		for(int k = 0; k < nb; k++) ok = ok && (h[pos + k] & 0xC0) == 0x80;
+		if(!ok) continue;
+		uint32_t crc = 0;
+		for(uint32_t b = 0; b < hl; b++) {
+			crc ^= h[b];
+			for(int j = 0; j < 8; j++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xffu : (crc << 1) & 0xffu;
+		}
+		if(crc != h[hl]) continue;
+		const unsigned slot = atomicAdd(count, 1u);
+		if(slot < cap) cand[slot] = p;
+	}
+}
+
 // ================================================================ k_dec_walk
-__global__ void __launch_bounds__(128) k_dec_walk(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets,
-                                                 int nframes, DecFrameMeta *__restrict__ meta)
+// A frame is the byte range [begins[f], ends[f]): exact (ends = begins + 1 of one offsets array) or, with P.loose_end, an upper bound.
+__global__ void __launch_bounds__(128) k_dec_walk(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ begins,
+                                                 const unsigned long long *__restrict__ ends, int nframes, DecFrameMeta *__restrict__ meta)
 {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if(f >= nframes) return;
-	const unsigned long long off = offsets[f];
-	const uint32_t len = (uint32_t)(offsets[f + 1] - off);
+	const unsigned long long off = begins[f];
+	const uint32_t len = (uint32_t)min(ends[f] - off, 0x0fffffffull);
 	DecFrameMeta M;
 	M.status = DEC_OK; M.blocksize = 0; M.channel_assignment = 0; M.channels = 0; M.frame_bytes = 0; M.frame_number_lo = 0; M.variable = 0; M.sample_rate = 0; M.max_order = 0;
 #pragma unroll
@@ -342,89 +414,98 @@ __device__ __forceinline__ void dec_lane_loop(BitRd &br, const bool live, const 
 	const uint32_t psamples = po ? (bs_lane >> po) : bs_lane;
 	uint32_t next_part = order, k = 0, raw = 0;
 	bool esc = false;
-	const int32_t lim = (int32_t)1 << (out_bps - 1);
-#pragma unroll 1
-	for(uint32_t i0 = 0; i0 < bs_max; i0 += MAXORD) {
-#pragma unroll
-		for(int u = 0; u < MAXORD; u++) {
-			const uint32_t i = i0 + (uint32_t)u;
-			const bool on = live && i < bs_lane;
-			int32_t x = 0;
-			if(on) {
-				if(type == 0) x = cval;                                   // CONSTANT
-				else if(type == 1) x = br.get_signed(sbps);              // VERBATIM
-				else if(i < order) x = warm[u];                          // warm-up (only in the first MAXORD samples)
-				else {
-					if(i == next_part) {                                  // a partition starts: parameter (+ escape width)
-						k = br.get(plen);
-						esc = k >= pesc;
-						if(esc) raw = br.get(5);
-						next_part = po ? (i / psamples + 1) * psamples : bs_lane;
-					}
-					int32_t r;
-					if(!esc) {
-						// deduplication/bitreader_read_rice_signed_block.c: unary MSBs, k LSBs, zig-zag
-						const uint32_t v = br.peek32();
-						uint32_t uu;
-						const uint32_t z = (uint32_t)__clz((int)v);
-						if(v != 0 && z + 1 + k <= 32u) {
-							uu = (z << k) | ((v << (z + 1)) >> (32u - k - (k == 0)) >> (k == 0));
-							br.consume(z + 1 + k);
-						}
-						else {
-							const uint32_t msbs = br.unary();
-							uu = (msbs << k) | (k ? br.get(k) : 0u);
-						}
-						r = (int32_t)(uu >> 1) ^ -(int32_t)(uu & 1u);
-					}
-					else r = raw ? br.get_signed(raw) : 0;
-					// prediction from the last `order` samples: x[i-1-j] sits in slot (u - 1 - j) mod MAXORD
-					int32_t pred;
-					if(WIDE && lane_wide) {
-						long long s0 = 0, s1 = 0;
-#pragma unroll
-						for(int j = 0; j < MAXORD; j += 2) {
-							s0 += (long long)q[j] * (long long)H[(u - 1 - j + 2 * MAXORD) % MAXORD];
-							if(j + 1 < MAXORD) s1 += (long long)q[j + 1] * (long long)H[(u - 2 - j + 2 * MAXORD) % MAXORD];
-						}
-						pred = (int32_t)((s0 + s1) >> shift);
+	const uint32_t lim = 1u << (out_bps - 1);
+	// how this lane's output is formed from its own value and its partner's (stream_decoder.c:3476-3527):
+	// 0 own value, 1 right = left - side, 2 left = side + right, 3 left of mid/side, 4 right of mid/side
+	const int omode = ch != 2 ? 0 : ca == 1 ? (cidx ? 1 : 0) : ca == 2 ? (cidx ? 0 : 2) : ca == 3 ? (cidx ? 4 : 3) : 0;
+	int32_t *op = dst;
+
+	// one sample; FIRST: the first MAXORD samples of the block, where warm-up samples may still come straight from the header
+	auto step = [&](auto first_tag, const int u, const uint32_t i) {
+		constexpr bool FIRST = decltype(first_tag)::value;
+		const bool on = live && i < bs_lane;
+		int32_t x = 0;
+		if(on) {
+			if(type == 0) x = cval;                                   // CONSTANT
+			else if(type == 1) x = br.get_signed(sbps);              // VERBATIM
+			else if(FIRST && i < order) x = warm[u];                 // warm-up
+			else {
+				if(i == next_part) {                                  // a partition starts: parameter (+ escape width)
+					k = br.get(plen);
+					esc = k >= pesc;
+					if(esc) raw = br.get(5);
+					next_part = po ? (i / psamples + 1) * psamples : bs_lane;
+				}
+				int32_t r;
+				if(!esc) {
+					// deduplication/bitreader_read_rice_signed_block.c: unary MSBs, k LSBs, zig-zag
+					const uint32_t v = br.peek32();
+					const uint32_t z = (uint32_t)__clz((int)v);
+					uint32_t uu;
+					if(v != 0 && z + 1 + k <= 32u) {
+						const uint32_t low = k ? ((v << (z + 1)) >> (32u - k)) : 0u;
+						uu = (z << k) | low;
+						br.consume(z + 1 + k);
 					}
 					else {
-						int s0 = 0, s1 = 0;
-#pragma unroll
-						for(int j = 0; j < MAXORD; j += 2) {
-							s0 += q[j] * H[(u - 1 - j + 2 * MAXORD) % MAXORD];
-							if(j + 1 < MAXORD) s1 += q[j + 1] * H[(u - 2 - j + 2 * MAXORD) % MAXORD];
-						}
-						pred = (s0 + s1) >> shift;
+						const uint32_t msbs = br.unary();
+						uu = (msbs << k) | (k ? br.get(k) : 0u);
 					}
-					x = r + pred;
+					r = (int32_t)(uu >> 1) ^ -(int32_t)(uu & 1u);
 				}
-				H[u] = x;
-			}
-			// ---- undo the channel decorrelation (stream_decoder.c:3476-3527) and store interleaved
-			const int32_t val = (int32_t)((uint32_t)x << wasted);
-			int32_t out = val;
-			if(ch == 2) {
-				const int32_t other = __shfl_xor_sync(0xffffffffu, val, 1);
-				if(ca == 1) out = cidx == 0 ? val : other - val;                       // left, side -> right = left - side
-				else if(ca == 2) out = cidx == 0 ? val + other : val;                  // side, right -> left = side + right
-				else if(ca == 3) {
-					const int32_t mid = cidx == 0 ? val : other, side = cidx == 0 ? other : val;
-					const int32_t m2 = (int32_t)(((uint32_t)mid << 1) | ((uint32_t)side & 1u));
-					out = cidx == 0 ? (m2 + side) >> 1 : (m2 - side) >> 1;
+				else r = raw ? br.get_signed(raw) : 0;
+				// prediction from the last `order` samples: x[i-1-j] sits in slot (u - 1 - j) mod MAXORD
+				int32_t pred;
+				if(WIDE && lane_wide) {
+					long long s0 = 0, s1 = 0;
+#pragma unroll
+					for(int j = 0; j < MAXORD; j += 2) {
+						s0 += (long long)q[j] * (long long)H[(u - 1 - j + 2 * MAXORD) % MAXORD];
+						if(j + 1 < MAXORD) s1 += (long long)q[j + 1] * (long long)H[(u - 2 - j + 2 * MAXORD) % MAXORD];
+					}
+					pred = (int32_t)((s0 + s1) >> shift);
 				}
+				else {
+					int s0 = 0, s1 = 0;
+#pragma unroll
+					for(int j = 0; j < MAXORD; j += 2) {
+						s0 += q[j] * H[(u - 1 - j + 2 * MAXORD) % MAXORD];
+						if(j + 1 < MAXORD) s1 += q[j + 1] * H[(u - 2 - j + 2 * MAXORD) % MAXORD];
+					}
+					pred = (s0 + s1) >> shift;
+				}
+				x = r + pred;
 			}
-			if(on) {
-				if(out < -lim || out >= lim) bad = true;  // stream_decoder.c:2458-2472 OUT_OF_BOUNDS
-				dst[(size_t)i * ch] = out;
-			}
+			H[u] = x;
 		}
+		// ---- undo the channel decorrelation and store interleaved
+		const int32_t val = (int32_t)((uint32_t)x << wasted);
+		int32_t out = val;
+		if(ch == 2) {
+			const int32_t other = __shfl_xor_sync(0xffffffffu, val, 1);
+			const int32_t m2a = (int32_t)(((uint32_t)val << 1) | ((uint32_t)other & 1u)), m2b = (int32_t)(((uint32_t)other << 1) | ((uint32_t)val & 1u));
+			out = omode == 0 ? val : omode == 1 ? other - val : omode == 2 ? val + other : omode == 3 ? (m2a + other) >> 1 : (m2b - val) >> 1;
+		}
+		if(on) {
+			if((uint32_t)out + lim >= 2u * lim) bad = true;  // stream_decoder.c:2458-2472 OUT_OF_BOUNDS
+			*op = out;
+		}
+		op += ch;
+	};
+	if(bs_max > 0) {
+#pragma unroll
+		for(int u = 0; u < MAXORD; u++) step(std::true_type{}, u, (uint32_t)u);
+	}
+#pragma unroll 1
+	for(uint32_t i0 = MAXORD; i0 < bs_max; i0 += MAXORD) {
+#pragma unroll
+		for(int u = 0; u < MAXORD; u++) step(std::false_type{}, u, i0 + (uint32_t)u);
 	}
 }
 
 template <int MAXQ>
-__global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets, int nframes,
+__global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ begins,
+                                                   const unsigned long long *__restrict__ ends, int nframes,
                                                    DecFrameMeta *__restrict__ meta, int32_t *__restrict__ pcm, unsigned long long capacity_samples,
                                                    uint32_t *__restrict__ status_out, DecSubframeInfo *__restrict__ subinfo)
 {
@@ -442,8 +523,8 @@ __global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__res
 	uint32_t len = 0;
 	if(f < nframes) {
 		M = meta[f];
-		off = offsets[f];
-		len = (uint32_t)(offsets[f + 1] - off);
+		off = begins[f];
+		len = (uint32_t)min(ends[f] - off, 0x0fffffffull);
 	}
 	const unsigned long long first = (unsigned long long)f * (unsigned long long)P.blocksize;
 	// this instantiation's share of the frames: MAXQ = 12 takes every frame whose predictors have at most 12 taps, MAXQ = 32 the rest
@@ -591,52 +672,112 @@ __device__ __forceinline__ uint32_t dec_gf16_mul(uint32_t a, uint32_t b)
 	return r;
 }
 
-// One warp per frame; lane l owns a contiguous chunk of bytes aligned to the end of the frame. Byte table in shared memory,
-// the tail of the chunk loop reads whole words when the frame start is word aligned... kept byte-wise: the frames of a
-// stream start at arbitrary byte offsets. Writes the final per-frame status word.
-__global__ void __launch_bounds__(128) k_dec_crc(const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ offsets,
-                                                int nframes, DecFrameMeta *__restrict__ meta, uint32_t *__restrict__ status_out)
+// Device table of the CRC-16 pass (uint16): [0, 1024) slicing-by-4 tables T[k][b] = CRC of byte b followed by k zero bytes;
+// [1024 + (Lw - 1) * 5 + s] = x^(32 Lw 2^s) mod (x^16+x^15+x^2+1) for Lw = 1..kDecCrcLw, s < 5: the multipliers that combine
+// the 32 lane CRCs of a frame (crc(A || B) = crc(A) x^|B| + crc(B), init 0).
+constexpr int kDecCrcLw = 1024;
+constexpr int kDecCrcTabEntries = 1024 + kDecCrcLw * 5;
+__global__ void k_dec_crc_tables(uint16_t *__restrict__ tab)
 {
-	__shared__ uint16_t s_tab[256];
-	for(int e = threadIdx.x; e < 256; e += blockDim.x) {
-		uint32_t c = (uint32_t)e << 8;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t < 256) {
+		uint32_t c = (uint32_t)t << 8;
 #pragma unroll
-		for(int j = 0; j < 8; j++) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) : (c << 1);
-		s_tab[e] = (uint16_t)c;
+		for(int j = 0; j < 8; j++) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) & 0xffffu : (c << 1) & 0xffffu;
+		uint32_t prev = c;
+		tab[t] = (uint16_t)c;
+		for(int k = 1; k < 4; k++) {
+			// one more zero byte: shift the 16-bit state through 8 zero bits
+			for(int j = 0; j < 8; j++) prev = (prev & 0x8000u) ? ((prev << 1) ^ 0x8005u) & 0xffffu : (prev << 1) & 0xffffu;
+			tab[k * 256 + t] = (uint16_t)prev;
+		}
 	}
+	if(t < kDecCrcLw * 5) {
+		const uint32_t Lw = (uint32_t)(t / 5) + 1u;
+		unsigned long long e = (32ull * Lw) << (t % 5);
+		uint32_t m = 1, bb = 2;  // x^e by square and multiply
+		while(e) {
+			if(e & 1ull) m = dec_gf16_mul(m, bb);
+			bb = dec_gf16_mul(bb, bb);
+			e >>= 1;
+		}
+		tab[1024 + t] = (uint16_t)m;
+	}
+}
+
+// One warp per frame; lane l owns Lw 4-byte groups ending (32 - l - 1) * Lw groups before the frame's last data byte. The
+// frame starts at an arbitrary byte address: a group is assembled from two aligned words with a funnel shift; groups that
+// would start in front of the frame are zero bytes, which a CRC with initial value 0 ignores -- so every lane runs the same
+// Lw slicing-by-4 steps with no alignment cases, and the combine multipliers depend on Lw only. Writes the final status.
+__global__ void __launch_bounds__(128) k_dec_crc(const uint8_t *__restrict__ frames, const unsigned long long *__restrict__ begins,
+                                                int nframes, DecFrameMeta *__restrict__ meta, uint32_t *__restrict__ status_out, uint32_t *__restrict__ bytes_out,
+                                                const uint16_t *__restrict__ crc_tab)
+{
+	__shared__ uint16_t s_tab[4 * 256];
+	for(int e = threadIdx.x; e < 4 * 256 / 2; e += blockDim.x) reinterpret_cast<uint32_t *>(s_tab)[e] = __ldg(reinterpret_cast<const uint32_t *>(crc_tab) + e);
 	__syncthreads();
 	const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
 	if(f >= nframes) return;
 	const DecFrameMeta M = meta[f];
 	if(M.status != DEC_OK) return;
-	const unsigned long long off = offsets[f];
+	const unsigned long long off = begins[f];
 	const uint32_t len = M.frame_bytes;
 	if(len < 3) return;
 	const uint32_t nbytes = len - 2;
 	const uint8_t *p = frames + off;
-	const uint32_t L = (nbytes + 31) / 32;
-	const long long cstart = (long long)nbytes - (long long)(32 - lane) * L, cend = cstart + L;
+	const uint32_t Lw = (nbytes + 127) / 128;                       // groups per lane
+	const long long first = (long long)nbytes - (long long)(32 - lane) * Lw * 4;  // frame offset of this lane's first byte (may be < 0)
+	const uintptr_t a0 = reinterpret_cast<uintptr_t>(p);
 	uint32_t crc = 0;
-	for(long long b = cstart < 0 ? 0 : cstart; b < cend; b++)
-		crc = ((crc << 8) & 0xffffu) ^ s_tab[((crc >> 8) ^ p[b]) & 0xffu];
-	// m = x^(8L) mod P, squared per tree level
-	uint32_t m = 1, bb = 2, e = 8 * L;
-	while(e) {
-		if(e & 1) m = dec_gf16_mul(m, bb);
-		bb = dec_gf16_mul(bb, bb);
-		e >>= 1;
+	// aligned word stream: word index relative to the aligned word holding frame byte 0
+	const uint32_t lead = (uint32_t)(a0 & 3);
+	const uint32_t *wbase = reinterpret_cast<const uint32_t *>(a0 - lead);
+	long long o = first;
+	// previous aligned word (big-endian) for the funnel; loaded lazily when the group touches the frame
+	uint32_t wprev = 0;
+	bool have_prev = false;
+	for(uint32_t g = 0; g < Lw; g++, o += 4) {
+		uint32_t x = 0;
+		if(o + 3 >= 0) {
+			// bytes o .. o+3 of the frame sit at byte (lead + o) of the aligned stream
+			const long long sb = (long long)lead + o;               // may be negative only by up to 3 when o < 0 <= o + 3
+			const long long wi = sb >= 0 ? (sb >> 2) : -1;
+			const uint32_t sh = (uint32_t)(sb & 3) * 8;
+			uint32_t w0;
+			if(wi < 0) w0 = 0;
+			else if(have_prev) w0 = wprev;
+			else w0 = __byte_perm(__ldg(wbase + wi), 0, 0x0123);
+			const uint32_t w1 = sh ? __byte_perm(__ldg(wbase + wi + 1), 0, 0x0123) : 0u;  // never past the CRC-16 bytes' word
+			x = sh ? __funnelshift_l(w1, w0, sh) : w0;
+			if(sh) { wprev = w1; have_prev = true; }
+			if(o < 0) x &= 0xffffffffu >> (8u * (uint32_t)(-o));      // bytes in front of the frame are zeros
+		}
+		crc = (uint32_t)s_tab[3 * 256 + (((crc >> 8) ^ (x >> 24)) & 0xffu)] ^ (uint32_t)s_tab[2 * 256 + ((crc ^ (x >> 16)) & 0xffu)] ^
+		      (uint32_t)s_tab[256 + ((x >> 8) & 0xffu)] ^ (uint32_t)s_tab[x & 0xffu];
 	}
 #pragma unroll
 	for(int s = 0; s < 5; s++) {
+		uint32_t m;
+		if(Lw <= (uint32_t)kDecCrcLw) m = __ldg(&crc_tab[1024 + (Lw - 1) * 5 + s]);
+		else {
+			unsigned long long e = (32ull * Lw) << s;
+			uint32_t bb = 2;
+			m = 1;
+			while(e) {
+				if(e & 1ull) m = dec_gf16_mul(m, bb);
+				bb = dec_gf16_mul(bb, bb);
+				e >>= 1;
+			}
+		}
 		const uint32_t other = __shfl_down_sync(0xffffffffu, crc, 1 << s);
 		if((lane & ((2 << s) - 1)) == 0) crc = dec_gf16_mul(crc, m) ^ other;
-		m = dec_gf16_mul(m, m);
 	}
 	if(lane == 0) {
 		const uint32_t want = ((uint32_t)p[nbytes] << 8) | p[nbytes + 1];
 		uint32_t st = DEC_OK;
 		if(crc != want) { st = DEC_CRC16; meta[f].status = DEC_CRC16; }
 		if(status_out) status_out[f] = st | (M.blocksize << 8);  // low byte: status, upper: decoded blocksize
+		if(bytes_out) bytes_out[f] = len;
 	}
 }
 

@@ -1,6 +1,7 @@
 // decoder.cu -- host side of the B200 FLAC batch frame decoder + its C ABI (include/flac_b200.h).
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "decode_kernels.cuh"
@@ -13,6 +14,7 @@ struct fb200_decoder {
 	uint32_t max_frames = 0;
 	DecK k{};
 	DecFrameMeta *d_meta = nullptr;
+	uint16_t *d_crc_tab = nullptr;     // slicing tables + combine multipliers of k_dec_crc
 	DecSubframeInfo *d_subinfo = nullptr;  // per (frame, channel), only when the client asked for subframe details
 	size_t d_subinfo_cap = 0;
 	bool want_subinfo = false;
@@ -26,6 +28,14 @@ struct fb200_decoder {
 	uint32_t *d_status = nullptr;
 	size_t d_status_cap = 0;
 	cudaStream_t stream = nullptr;
+	std::vector<uint32_t> h_status;   // per-frame status words of the last host decode
+	uint8_t *d_stream = nullptr;      // staging of fb200_decoder_index_host / fb200_decode_stream_host
+	size_t d_stream_cap = 0;
+	unsigned long long *d_cand = nullptr;
+	size_t d_cand_cap = 0;
+	unsigned *d_count = nullptr;
+	uint32_t *d_fbytes = nullptr;
+	size_t d_fbytes_cap = 0;
 	uint64_t launches = 0;
 	bool prof_on = false;
 	std::vector<cudaEvent_t> prof_events;
@@ -84,11 +94,18 @@ int fb200_decoder_create(const fb200_decoder_config *cfg, int device, uint32_t m
 	d->k.channels = (int)cfg->channels; d->k.bps = (int)cfg->bits_per_sample; d->k.sample_rate = (int)cfg->sample_rate;
 	d->k.blocksize = (int)cfg->blocksize;
 	d->k.loose_end = 0;
-	if(cudaMalloc(&d->d_meta, (size_t)d->max_frames * sizeof(DecFrameMeta)) != cudaSuccess ||
+	if(cudaMalloc(&d->d_crc_tab, (size_t)kDecCrcTabEntries * sizeof(uint16_t)) != cudaSuccess ||
+	   cudaMalloc(&d->d_meta, (size_t)d->max_frames * sizeof(DecFrameMeta)) != cudaSuccess ||
 	   cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
 		set_error("decoder workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
 		fb200_decoder_destroy(d);
 		return FB200_ERR_ALLOC;
+	}
+	k_dec_crc_tables<<<(kDecCrcLw * 5 + 255) / 256, 256, 0, d->stream>>>(d->d_crc_tab);
+	if(cudaStreamSynchronize(d->stream) != cudaSuccess) {
+		set_error("decoder table kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+		fb200_decoder_destroy(d);
+		return FB200_ERR_CUDA;
 	}
 	*out = d;
 	return FB200_OK;
@@ -98,7 +115,7 @@ void fb200_decoder_destroy(fb200_decoder *d)
 {
 	if(!d) return;
 	cudaSetDevice(d->device);
-	cudaFree(d->d_subinfo); cudaFree(d->d_meta); cudaFree(d->d_frames); cudaFree(d->d_offsets); cudaFree(d->d_pcm); cudaFree(d->d_status);
+	cudaFree(d->d_subinfo); cudaFree(d->d_meta); cudaFree(d->d_crc_tab); cudaFree(d->d_stream); cudaFree(d->d_cand); cudaFree(d->d_count); cudaFree(d->d_fbytes); cudaFree(d->d_frames); cudaFree(d->d_offsets); cudaFree(d->d_pcm); cudaFree(d->d_status);
 	if(d->stream) cudaStreamDestroy(d->stream);
 	delete d;
 }
@@ -127,16 +144,15 @@ int fb200_decoder_get_profile(fb200_decoder *d, double ms[FB200_DPROF_KERNELS], 
 	return FB200_OK;
 }
 
-int fb200_decode_device(fb200_decoder *d, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,
-                        int32_t *d_pcm, uint64_t pcm_capacity_samples, uint32_t *d_frame_status, void *cuda_stream, int sync)
+// frames f = 0..nframes-1 occupy [begins[f], ends[f]) of d_frames (device arrays); loose: the ends are upper bounds
+static int decode_ranges(fb200_decoder *d, const uint8_t *d_frames, const unsigned long long *begins, const unsigned long long *ends, uint32_t nframes,
+                         int32_t *d_pcm, uint64_t pcm_capacity_samples, uint32_t *d_frame_status, uint32_t *d_frame_bytes, int loose, cudaStream_t st)
 {
-	if(!d || !d_frames || !d_frame_offsets || !d_pcm) return FB200_ERR_INVALID;
-	FB_CUDA(cudaSetDevice(d->device));
-	cudaStream_t st = (cudaStream_t)cuda_stream;
-	const unsigned long long *offs = reinterpret_cast<const unsigned long long *>(d_frame_offsets);
 	const int ch = (int)d->cfg.channels;
 	const int chl = ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : 8;
 	const int fpw = 32 / chl;
+	DecK k = d->k;
+	k.loose_end = loose;
 	if(d->want_subinfo && (size_t)nframes * ch > d->d_subinfo_cap) {
 		cudaFree(d->d_subinfo); d->d_subinfo = nullptr; d->d_subinfo_cap = 0;
 		FB_CUDA(cudaMalloc(&d->d_subinfo, (size_t)nframes * ch * sizeof(DecSubframeInfo)));
@@ -145,27 +161,40 @@ int fb200_decode_device(fb200_decoder *d, const uint8_t *d_frames, const uint64_
 	uint32_t done = 0;
 	while(done < nframes) {
 		const int nf = (int)((nframes - done) < d->max_frames ? (nframes - done) : d->max_frames);
-		// offsets are absolute into d_frames; frame `done + i` decodes to sample offset (done + i) * blocksize
+		// frame `done + i` decodes to sample offset (done + i) * blocksize
 		const unsigned long long used = (unsigned long long)done * d->cfg.blocksize;
 		const unsigned long long cap_left = pcm_capacity_samples > used ? pcm_capacity_samples - used : 0ull;  // frames that do not fit are reported (DEC_LENGTH), never written
 		dprof_mark(d, -1, st);
-		k_dec_walk<<<(nf + 127) / 128, 128, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_meta);
+		k_dec_walk<<<(nf + 127) / 128, 128, 0, st>>>(k, d_frames, begins + done, ends + done, nf, d->d_meta);
 		dprof_mark(d, FB200_DPROF_WALK, st);
 		const int warps = (nf + fpw - 1) / fpw;
 		// predictors of at most 12 taps (every preset) and the rest (-l 13..32): two instantiations, each taking its frames
-		k_dec_frames<12><<<(warps + 3) / 4, 128, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
+		k_dec_frames<12><<<(warps + 3) / 4, 128, 0, st>>>(k, d_frames, begins + done, ends + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
 		                                                 d_frame_status ? d_frame_status + done : nullptr,
 		                                                 d->want_subinfo ? d->d_subinfo + (size_t)done * ch : nullptr);
-		k_dec_frames<32><<<(warps + 3) / 4, 128, 0, st>>>(d->k, d_frames, offs + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
+		k_dec_frames<32><<<(warps + 3) / 4, 128, 0, st>>>(k, d_frames, begins + done, ends + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
 		                                                 d_frame_status ? d_frame_status + done : nullptr,
 		                                                 d->want_subinfo ? d->d_subinfo + (size_t)done * ch : nullptr);
 		dprof_mark(d, FB200_DPROF_FRAMES, st);
-		k_dec_crc<<<(nf + 3) / 4, 128, 0, st>>>(d_frames, offs + done, nf, d->d_meta, d_frame_status ? d_frame_status + done : nullptr);
+		k_dec_crc<<<(nf + 3) / 4, 128, 0, st>>>(d_frames, begins + done, nf, d->d_meta, d_frame_status ? d_frame_status + done : nullptr,
+		                                       d_frame_bytes ? d_frame_bytes + done : nullptr, d->d_crc_tab);
 		dprof_mark(d, FB200_DPROF_CRC, st);
 		d->launches += 4;
 		done += nf;
 	}
 	FB_CUDA(cudaGetLastError());
+	return FB200_OK;
+}
+
+int fb200_decode_device(fb200_decoder *d, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,
+                        int32_t *d_pcm, uint64_t pcm_capacity_samples, uint32_t *d_frame_status, void *cuda_stream, int sync)
+{
+	if(!d || !d_frames || !d_frame_offsets || !d_pcm) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(d->device));
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	const unsigned long long *offs = reinterpret_cast<const unsigned long long *>(d_frame_offsets);
+	const int rc = decode_ranges(d, d_frames, offs, offs + 1, nframes, d_pcm, pcm_capacity_samples, d_frame_status, nullptr, 0, st);
+	if(rc != FB200_OK) return rc;
 	if(sync) FB_CUDA(cudaStreamSynchronize(st));
 	return FB200_OK;
 }
@@ -208,11 +237,11 @@ int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *f
 	                                   d->d_status, d->stream, 0);
 	if(rc != FB200_OK) return rc;
 	FB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm, (size_t)cap * d->cfg.channels * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
-	uint32_t *h_status = new uint32_t[nframes];
+	d->h_status.resize(nframes);
+	uint32_t *h_status = d->h_status.data();
 	cudaError_t ce = cudaMemcpyAsync(h_status, d->d_status, (size_t)nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream);
 	if(ce == cudaSuccess) ce = cudaStreamSynchronize(d->stream);
 	if(ce != cudaSuccess) {
-		delete[] h_status;
 		set_error("decode: %s", cudaGetErrorString(ce));
 		return FB200_ERR_CUDA;
 	}
@@ -223,13 +252,122 @@ int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *f
 			bad++;
 		}
 	const uint64_t last_bs = h_status[nframes - 1] >> 8;
-	delete[] h_status;
 	if(bad_frames) *bad_frames = bad;
 	if(samples_decoded) {
 		const uint64_t n = (uint64_t)(nframes - 1) * d->cfg.blocksize + last_bs;
 		*samples_decoded = n < cap ? n : cap;
 	}
 	if(bad) set_error("%u of %u frames failed to decode (first: frame %u, status %u)", bad, nframes, first_bad, first_code);
+	return FB200_OK;
+}
+
+
+int fb200_decoder_get_frame_status(const fb200_decoder *d, uint32_t *status, uint32_t nframes)
+{
+	if(!d || !status) return FB200_ERR_INVALID;
+	if(nframes > d->h_status.size()) { set_error("only %zu frames were decoded by the last call", d->h_status.size()); return FB200_ERR_INVALID; }
+	memcpy(status, d->h_status.data(), (size_t)nframes * sizeof(uint32_t));
+	return FB200_OK;
+}
+
+int fb200_decoder_enable_subframe_info(fb200_decoder *d, int on)
+{
+	if(!d) return FB200_ERR_INVALID;
+	d->want_subinfo = on != 0;
+	return FB200_OK;
+}
+
+int fb200_decoder_get_subframe_info(fb200_decoder *d, fb200_subframe_info *info, uint32_t nframes)
+{
+	if(!d || !info) return FB200_ERR_INVALID;
+	static_assert(sizeof(fb200_subframe_info) == sizeof(DecSubframeInfo), "public and device subframe records must match");
+	if(!d->want_subinfo || (size_t)nframes * d->cfg.channels > d->d_subinfo_cap) { set_error("subframe details were not collected for %u frames", nframes); return FB200_ERR_INVALID; }
+	FB_CUDA(cudaSetDevice(d->device));
+	FB_CUDA(cudaMemcpy(info, d->d_subinfo, (size_t)nframes * d->cfg.channels * sizeof(DecSubframeInfo), cudaMemcpyDeviceToHost));
+	return FB200_OK;
+}
+
+// The decoder front end for a whole stream (frame_sync_ + read_frame_header_ for every byte position at once): offsets of
+// every position that carries a sync code and a self-consistent frame header, ascending.
+int fb200_decoder_index_host(fb200_decoder *d, const uint8_t *stream, uint64_t nbytes, uint64_t *candidates, uint32_t capacity, uint32_t *ncandidates)
+{
+	if(!d || (!stream && nbytes) || !candidates || !ncandidates) return FB200_ERR_INVALID;
+	FB_CUDA(cudaSetDevice(d->device));
+	*ncandidates = 0;
+	if(nbytes < 6) return FB200_OK;
+	if(nbytes + 64 > d->d_stream_cap) {
+		cudaFree(d->d_stream); d->d_stream = nullptr; d->d_stream_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_stream, nbytes + 64));
+		d->d_stream_cap = nbytes + 64;
+	}
+	if(capacity > d->d_cand_cap) {
+		cudaFree(d->d_cand); d->d_cand = nullptr; d->d_cand_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_cand, (size_t)capacity * sizeof(unsigned long long)));
+		d->d_cand_cap = capacity;
+	}
+	if(!d->d_count) FB_CUDA(cudaMalloc(&d->d_count, sizeof(unsigned)));
+	FB_CUDA(cudaMemcpyAsync(d->d_stream, stream, nbytes, cudaMemcpyHostToDevice, d->stream));
+	FB_CUDA(cudaMemsetAsync(d->d_stream + nbytes, 0, 64, d->stream));
+	FB_CUDA(cudaMemsetAsync(d->d_count, 0, sizeof(unsigned), d->stream));
+	k_dec_scan<<<148 * 8, 256, 0, d->stream>>>(d->d_stream, nbytes, d->d_cand, capacity, d->d_count);
+	d->launches++;
+	unsigned n = 0;
+	FB_CUDA(cudaMemcpyAsync(&n, d->d_count, sizeof n, cudaMemcpyDeviceToHost, d->stream));
+	FB_CUDA(cudaStreamSynchronize(d->stream));
+	if(n > capacity) { set_error("more than %u frame header candidates", capacity); return FB200_ERR_OUTPUT_TOO_SMALL; }
+	FB_CUDA(cudaMemcpy(candidates, d->d_cand, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	std::sort(candidates, candidates + n);
+	*ncandidates = n;
+	return FB200_OK;
+}
+
+// Decode the frames that START at begins[i] of the stream last given to fb200_decoder_index_host (still resident on the
+// device); frame i may extend at most to begins[i] + max_frame_bytes (or the end of the stream): its true length comes out
+// of the parse (frame_bytes[i]) and its CRC-16 is checked over exactly that. Frame i lands at sample offset i * blocksize.
+int fb200_decode_indexed_host(fb200_decoder *d, const uint64_t *begins, uint32_t nframes, uint32_t max_frame_bytes, uint64_t stream_bytes,
+                              int32_t *pcm, uint64_t pcm_capacity_samples, uint32_t *frame_status, uint32_t *frame_bytes)
+{
+	if(!d || !begins || !pcm || !frame_status || !frame_bytes) return FB200_ERR_INVALID;
+	if(!d->d_stream || stream_bytes + 64 > d->d_stream_cap) { set_error("no indexed stream is resident"); return FB200_ERR_INVALID; }
+	FB_CUDA(cudaSetDevice(d->device));
+	if(nframes == 0) return FB200_OK;
+	const uint64_t need_samples = (uint64_t)nframes * d->cfg.blocksize;
+	const uint64_t cap = pcm_capacity_samples < need_samples ? pcm_capacity_samples : need_samples;
+	if(2 * (size_t)nframes > d->d_offsets_cap) {
+		cudaFree(d->d_offsets); d->d_offsets = nullptr; d->d_offsets_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_offsets, 2 * (size_t)nframes * sizeof(unsigned long long)));
+		d->d_offsets_cap = 2 * (size_t)nframes;
+	}
+	if(need_samples * d->cfg.channels > d->d_pcm_cap) {
+		cudaFree(d->d_pcm); d->d_pcm = nullptr; d->d_pcm_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_pcm, need_samples * d->cfg.channels * sizeof(int32_t)));
+		d->d_pcm_cap = need_samples * d->cfg.channels;
+	}
+	if(nframes > d->d_status_cap) {
+		cudaFree(d->d_status); d->d_status = nullptr; d->d_status_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_status, (size_t)nframes * sizeof(uint32_t)));
+		d->d_status_cap = nframes;
+	}
+	if(nframes > d->d_fbytes_cap) {
+		cudaFree(d->d_fbytes); d->d_fbytes = nullptr; d->d_fbytes_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_fbytes, (size_t)nframes * sizeof(uint32_t)));
+		d->d_fbytes_cap = nframes;
+	}
+	std::vector<unsigned long long> be(2 * (size_t)nframes);
+	for(uint32_t i = 0; i < nframes; i++) {
+		be[i] = begins[i];
+		const unsigned long long e = begins[i] + max_frame_bytes;
+		be[nframes + i] = e < stream_bytes ? e : stream_bytes;
+	}
+	FB_CUDA(cudaMemcpyAsync(d->d_offsets, be.data(), be.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, d->stream));
+	FB_CUDA(cudaMemsetAsync(d->d_fbytes, 0, (size_t)nframes * sizeof(uint32_t), d->stream));
+	const int rc = decode_ranges(d, d->d_stream, d->d_offsets, d->d_offsets + nframes, nframes, d->d_pcm, need_samples, d->d_status, d->d_fbytes, 1, d->stream);
+	if(rc != FB200_OK) return rc;
+	FB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm, (size_t)cap * d->cfg.channels * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+	FB_CUDA(cudaMemcpyAsync(frame_status, d->d_status, (size_t)nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+	FB_CUDA(cudaMemcpyAsync(frame_bytes, d->d_fbytes, (size_t)nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+	FB_CUDA(cudaStreamSynchronize(d->stream));
+	d->h_status.assign(frame_status, frame_status + nframes);
 	return FB200_OK;
 }
 

@@ -7,13 +7,23 @@ template <int MO>
 static void emit3(const EncK &k, int rt, size_t smem, const Emit3Args &a, int nb, cudaStream_t st)
 {
 	const int nt = (k.bs / rt) * k.channels;
-	if(rt == 32) {
-		if(k.channels == 2) k_emit3<32, MO, 2><<<nb, nt, smem, st>>>(k, a);
-		else k_emit3<32, MO, 1><<<nb, nt, smem, st>>>(k, a);
+	if(k.bps > 16) {
+		if(rt == 32) {
+			if(k.channels == 2) k_emit3<32, MO, 2, true><<<nb, nt, smem, st>>>(k, a);
+			else k_emit3<32, MO, 1, true><<<nb, nt, smem, st>>>(k, a);
+		}
+		else {
+			if(k.channels == 2) k_emit3<36, MO, 2, true><<<nb, nt, smem, st>>>(k, a);
+			else k_emit3<36, MO, 1, true><<<nb, nt, smem, st>>>(k, a);
+		}
+	}
+	else if(rt == 32) {
+		if(k.channels == 2) k_emit3<32, MO, 2, false><<<nb, nt, smem, st>>>(k, a);
+		else k_emit3<32, MO, 1, false><<<nb, nt, smem, st>>>(k, a);
 	}
 	else {
-		if(k.channels == 2) k_emit3<36, MO, 2><<<nb, nt, smem, st>>>(k, a);
-		else k_emit3<36, MO, 1><<<nb, nt, smem, st>>>(k, a);
+		if(k.channels == 2) k_emit3<36, MO, 2, false><<<nb, nt, smem, st>>>(k, a);
+		else k_emit3<36, MO, 1, false><<<nb, nt, smem, st>>>(k, a);
 	}
 }
 
@@ -29,10 +39,14 @@ void launch_crc16_tables(uint16_t *tab, cudaStream_t st) { k_crc16_tables<<<1, 2
 template <int MO>
 static void emit3_attrs()
 {
-	cudaFuncSetAttribute(k_emit3<32, MO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	cudaFuncSetAttribute(k_emit3<32, MO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	cudaFuncSetAttribute(k_emit3<36, MO, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-	cudaFuncSetAttribute(k_emit3<36, MO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<32, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<32, MO, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<36, MO, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<36, MO, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<32, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<32, MO, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<36, MO, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	cudaFuncSetAttribute(k_emit3<36, MO, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 void emit3_init(int)

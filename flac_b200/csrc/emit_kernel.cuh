@@ -159,8 +159,10 @@ __device__ __forceinline__ void group_residual_wide(const int (&xg)[MAXORD + G],
 
 // R_T: samples per run (32 or 36); MAXORD: 8 / 12 / 32; CH: channels in the stream (1 or 2).
 // blockDim.x = NT = (bs / R_T) * CH <= 256 (a power of two, TPC = bs / R_T >= 32).
-template <int R_T, int MAXORD, int CH>
-__global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
+// WIDEK: the stream is deeper than 16 bits, i.e. a predictor may need 64-bit accumulation (lpc.c:786-884); the 16-bit
+// instantiations carry no wide code and fit four CTAs per SM.
+template <int R_T, int MAXORD, int CH, bool WIDEK>
+__global__ void __launch_bounds__(256, WIDEK ? 3 : 4) k_emit3(EncK P, Emit3Args A)
 {
 	static_assert(R_T == 32 || R_T == 36, "run length");
 	static_assert(CH == 1 || CH == 2, "resident emit path: 1 or 2 channels");
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 	Emit3Shared &S = *reinterpret_cast<Emit3Shared *>(smem_raw);
 	int32_t *const planar = reinterpret_cast<int32_t *>(smem_raw + (sizeof(Emit3Shared) + 15) / 16 * 16);
 	uint32_t *const words = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(planar) + emit3_sig_bytes(bs, R_T, CH));
-	const int words_cap = P.slot_words + 8;
+	const int words_cap = P.emit3_words + 8;
 	uint16_t *const crc_tab = reinterpret_cast<uint16_t *>(planar);  // loaded after the pack pass, when the signals are dead
 	uint64_t *const mbar = reinterpret_cast<uint64_t *>(&S.mbar);
 
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 		}
 		const int qshift = type == SF_FIXED ? 0 : shift;
 		constexpr int NT12 = MAXORD < 12 ? MAXORD : 12;
-		const int cls = wide ? (order <= 8 ? 4 : 5) : (order <= 4 ? 0 : order <= 8 ? 1 : (MAXORD > 8 && order <= 12) ? 2 : 3);
+		const int cls = (WIDEK && wide) ? (order <= 8 ? 4 : 5) : (order <= 4 ? 0 : order <= 8 ? 1 : (MAXORD > 8 && order <= 12) ? 2 : 3);
 		int p = base / psize;
 		int next = (p + 1) * psize;
 		uint32_t k = __ldg(&pl->params[p]);
@@ -414,8 +416,8 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 				case 1: group_residual_narrow<G, MAXORD, 8>(xg, q, qshift, r); break;
 				case 2: group_residual_narrow<G, MAXORD, NT12>(xg, q, qshift, r); break;
 				case 3: group_residual_narrow<G, MAXORD, MAXORD>(xg, q, qshift, r); break;
-				case 4: group_residual_wide<G, MAXORD, 8>(xg, q, qshift, r); break;
-				default: group_residual_wide<G, MAXORD, MAXORD>(xg, q, qshift, r); break;
+				case 4: if(WIDEK) group_residual_wide<G, MAXORD, 8>(xg, q, qshift, r); break;
+				default: if(WIDEK) group_residual_wide<G, MAXORD, MAXORD>(xg, q, qshift, r); break;
 			}
 			uint32_t u[G];
 #pragma unroll
@@ -512,88 +514,106 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 			const uint32_t w = sh ? __funnelshift_r(lo, hi, sh) : lo;  // the header bytes shifted right by s0 bytes
 			if(w) atomicOr(&words[lane], w);
 		}
-		// subframe header fields: the first warp of a channel writes them, every field from its own lane
-		if(run < 32) {
-			const uint32_t sf0 = bit0 + __shfl_sync(0xffffffffu, start, 0);  // first bit of the subframe
-			const uint32_t warm0 = sf0 + kSubframeHeaderBits + (uint32_t)wasted;
-			const uint32_t after_warm = warm0 + (uint32_t)order * (uint32_t)sbps;
+		// subframe header fields (stream_encoder_framing.c:393-520): one field per thread, spread over the CTA so that no warp
+		// carries the whole header on top of its runs. Slots per channel: 0 type byte + wasted-bits unary (+ the constant),
+		// 1 precision + shift, 2 entropy method + partition order, 3.. warm-up samples, 35.. coefficients.
+		for(int g = tid; g < 72 * CH; g += NT) {
+			const int c = g / 72, slot = g - c * 72;
+			const SubframePlan *pc = bp + (c ? sidx1 : sidx0);
+			const int ftype = __ldg(&pc->type), forder = __ldg(&pc->order), fwasted = __ldg(&pc->wasted), fsbps = __ldg(&pc->bps);
+			const bool fpred = ftype == SF_FIXED || ftype == SF_LPC;
+			// first bit of the subframe: the exclusive prefix of its first run = the totals of the warps in front of it
+			uint32_t sf0 = bit0 + header_bits;
+			for(int w = 0; w < c * (TPC >> 5); w++) sf0 += S.scan[w];
+			const uint32_t warm0 = sf0 + kSubframeHeaderBits + (uint32_t)fwasted;
+			const uint32_t after_warm = warm0 + (uint32_t)forder * (uint32_t)fsbps;
 			BitPut bw;
-			if(run == 0) {
+			if(slot == 0) {
 				uint32_t tb;
-				switch(type) {
+				switch(ftype) {
 					case SF_CONSTANT: tb = 0x00; break;
 					case SF_VERBATIM: tb = 0x02; break;
-					case SF_FIXED: tb = 0x10 | ((uint32_t)order << 1); break;
-					default: tb = 0x40 | ((uint32_t)(order - 1) << 1); break;
+					case SF_FIXED: tb = 0x10 | ((uint32_t)forder << 1); break;
+					default: tb = 0x40 | ((uint32_t)(forder - 1) << 1); break;
 				}
 				bw.init(words, sf0);
-				bw.put(tb | (wasted ? 1u : 0u), 8);
-				if(wasted) { bw.skip((uint32_t)wasted - 1); bw.put(1, 1); }
-				if(type == SF_CONSTANT) bw.put(mask_bits(S.warm[myc][0], (uint32_t)sbps), (uint32_t)sbps);
+				bw.put(tb | (fwasted ? 1u : 0u), 8);
+				if(fwasted) { bw.skip((uint32_t)fwasted - 1); bw.put(1, 1); }
+				if(ftype == SF_CONSTANT) bw.put(mask_bits(S.warm[c][0], (uint32_t)fsbps), (uint32_t)fsbps);
 				bw.finish();
-				if(predicted) {
+			}
+			else if(slot == 1) {
+				if(ftype == SF_LPC) {
 					bw.init(words, after_warm);
-					if(type == SF_LPC) {
-						bw.put((uint32_t)precision - 1, kQlpPrecisionLen);
-						bw.put(mask_bits(shift, kQlpShiftLen), kQlpShiftLen);
-						bw.finish();
-						bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)order * (uint32_t)precision);
-					}
-					bw.put((uint32_t)method, kEntropyTypeLen);
-					bw.put((uint32_t)po, kRiceOrderLen);
+					bw.put((uint32_t)__ldg(&pc->precision) - 1, kQlpPrecisionLen);
+					bw.put(mask_bits(__ldg(&pc->shift), kQlpShiftLen), kQlpShiftLen);
 					bw.finish();
 				}
 			}
-			if(predicted) {
-				for(int i = run; i < order; i += 32) {
-					bw.init(words, warm0 + (uint32_t)i * (uint32_t)sbps);
-					bw.put(mask_bits(S.warm[myc][i], (uint32_t)sbps), (uint32_t)sbps);
+			else if(slot == 2) {
+				if(fpred) {
+					const uint32_t fprec = (uint32_t)__ldg(&pc->precision);
+					bw.init(words, after_warm + (ftype == SF_LPC ? kQlpPrecisionLen + kQlpShiftLen + (uint32_t)forder * fprec : 0u));
+					bw.put((uint32_t)__ldg(&pc->method), kEntropyTypeLen);
+					bw.put((uint32_t)__ldg(&pc->porder), kRiceOrderLen);
 					bw.finish();
 				}
-				if(type == SF_LPC) {
-					for(int i = run; i < order; i += 32) {
-						bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)i * (uint32_t)precision);
-						bw.put(mask_bits(__ldg(&pl->qlp[i]), (uint32_t)precision), (uint32_t)precision);
-						bw.finish();
-					}
+			}
+			else if(slot < 3 + FB200_MAX_LPC_ORDER) {
+				const int i = slot - 3;
+				if(fpred && i < forder) {
+					bw.init(words, warm0 + (uint32_t)i * (uint32_t)fsbps);
+					bw.put(mask_bits(S.warm[c][i], (uint32_t)fsbps), (uint32_t)fsbps);
+					bw.finish();
+				}
+			}
+			else {
+				const int i = slot - 3 - FB200_MAX_LPC_ORDER;
+				if(ftype == SF_LPC && i < forder) {
+					const uint32_t fprec = (uint32_t)__ldg(&pc->precision);
+					bw.init(words, after_warm + kQlpPrecisionLen + kQlpShiftLen + (uint32_t)i * fprec);
+					bw.put(mask_bits(__ldg(&pc->qlp[i]), fprec), fprec);
+					bw.finish();
 				}
 			}
 		}
 		// residual codes of this run (stream_encoder_framing.c:538-594, bitwriter.c:575-706)
 		if(predicted) {
-			if(one_partition && base >= order) {
-				// every sample of the run is a residual of ONE partition; the parameter field, if the partition starts here,
-				// goes first. Hot loop: zeros + stop bit + k low bits as one field of n = q + k + 1 bits; the pending word
-				// `cur` (fill bits used) spills into `words` when it completes. Only the run's first word can be shared with
-				// the previous run: it is kept in `fw` and OR-ed in at the end, so the loop has plain stores only.
+			if(one_partition) {
+				// ONE partition per run: zeros + stop bit + k low bits go out as one field of n = q + k + 1 bits; the pending word
+				// `cur` (fill bits used) spills into `words` when it completes. Only the run's first word can be shared with the
+				// previous run: it is kept in `fw` and OR-ed in at the end, so the loop has plain stores only. Every run -- the one
+				// with the warm-up samples included -- runs this same loop (skipn leading samples are not residuals; the partition
+				// parameter goes in front of sample prel), so the warps of a frame finish together.
 				const uint32_t k = k_run, k1 = k + 1;
 				const uint32_t stop = 1u << k, lowmask = stop - 1u;
-				uint32_t pos = bit0 + start + pre;
-				const int wfirst = (int)(pos >> 5);
-				int widx = wfirst;
-				uint32_t fill = pos & 31u, cur = 0, fw = 0;
-				bool fw_set = false;
+				const uint32_t pos0 = bit0 + start + pre;
+				const int w0 = (int)(pos0 >> 5);
+				int widx = w0, wshared = w0;
+				uint32_t fill = pos0 & 31u, cur = 0, fw = 0;
 				auto put = [&](uint32_t val, uint32_t n) {  // 1 <= n <= 32, val < 2^n
 					const unsigned long long t = (unsigned long long)val << (64u - fill - n);
 					cur |= (uint32_t)(t >> 32);
 					fill += n;
 					if(fill >= 32u) {
-						if(widx != wfirst) words[widx] = cur;
-						else { fw = cur; fw_set = true; }
+						if(widx != wshared) words[widx] = cur;
+						else { fw = cur; wshared = -1; }
 						widx++;
 						cur = (uint32_t)t;
 						fill -= 32u;
 					}
 				};
-				{
-					const int pidx = base / psize;
-					if(base == (pidx == 0 ? order : pidx * psize)) put(k, plen);  // the partition's first residual is this run's first sample
-				}
+				const int pidx = base / psize;
+				const int skipn = order > base ? order - base : 0;                       // leading warm-up samples of this run
+				const int prel = (pidx == 0 ? order : pidx * psize) - base;               // the partition's first residual, relative to the run
 #pragma unroll 1
 				for(int v4 = 0; v4 < R_T / 4; v4++) {
 					const uint4 uv = *reinterpret_cast<const uint4 *>(rowp + 4 * v4);
 #pragma unroll
 					for(int e = 0; e < 4; e++) {
+						const int m = 4 * v4 + e;
+						if(m < skipn) continue;
+						if(m == prel) put(k, plen);
 						const uint32_t u = e == 0 ? uv.x : e == 1 ? uv.y : e == 2 ? uv.z : uv.w;
 						const uint32_t qz = u >> k;
 						const uint32_t val = stop | (u & lowmask);
@@ -607,27 +627,8 @@ __global__ void __launch_bounds__(256, 3) k_emit3(EncK P, Emit3Args A)
 					}
 				}
 				// the run's first word (shared with the previous run) and its last, partial word (shared with the next)
-				if(fw_set) { if(fw) atomicOr(&words[wfirst], fw); if(cur) atomicOr(&words[widx], cur); }
+				if(wshared < 0) { if(fw) atomicOr(&words[w0], fw); if(cur) atomicOr(&words[widx], cur); }
 				else if(cur) atomicOr(&words[widx], cur);
-			}
-			else if(one_partition) {
-				// the run that contains the warm-up samples / the first residual of partition 0
-				RunPacker pk;
-				pk.init(words, bit0 + start + pre);
-				const uint32_t k = k_run;
-				const uint32_t stop = 1u << k, lowmask = stop - 1u;
-#pragma unroll 1
-				for(int m = 0; m < R_T; m++) {
-					const int i = base + m;
-					if(i >= order) {
-						if(i == order) pk.put(k, plen);
-						const uint32_t u = (uint32_t)rowp[m];
-						const uint32_t qz = u >> k;
-						pk.skip(qz);
-						pk.put(stop | (u & lowmask), k + 1);
-					}
-				}
-				pk.finish();
 			}
 			else {
 				// partitions shorter than a run (partition orders above log2(bs / R_T)): the parameter changes inside the run

@@ -247,46 +247,65 @@ __device__ __forceinline__ double expected_bits_scale(double lpc_error, double e
 	return 0.0;
 }
 
-// lpc.c:176-218 FLAC__lpc_compute_lp_coefficients. Runs the recursion up to max_order (or
-// until the error hits 0.0), records the error per order and, when want_order > 0, the float
-// predictor coefficients of that order. Returns the effective max order.
-__device__ int levinson(const double *ac, int max_order, int want_order, double *err_out, float *coef_out)
+// lpc.c:176-218 FLAC__lpc_compute_lp_coefficients. Runs the recursion up to max_order (or until the error hits 0.0),
+// records the error per order and, when want_order > 0, the float predictor coefficients of that order. Returns the
+// effective max order. Every loop is unrolled to the template bound MO with the live range as a predicate, so the
+// working arrays stay in registers (round 1's run-time indexed version kept 1 KB of them in local memory per thread:
+// 52 % long-scoreboard stalls). The arithmetic -- operations and their order -- is the reference's, statement by statement.
+template <int MO>
+__device__ __forceinline__ int levinson(const double (&ac)[MO + 1], int max_order, int want_order, double (&err_out)[MO], float (&coef_out)[MO])
 {
-	double lpc[FB200_MAX_LPC_ORDER];
+	double lpc[MO];
+#pragma unroll
+	for(int j = 0; j < MO; j++) lpc[j] = 0.0;
 	double err = ac[0];
-	for(int i = 0; i < max_order; i++) {
-		double r = -ac[i + 1];
-		for(int j = 0; j < i; j++) r -= lpc[j] * ac[i - j];
-		r /= err;
-		lpc[i] = r;
-		int j = 0;
-		for(; j < (i >> 1); j++) {
-			const double tmp = lpc[j];
-			lpc[j] += r * lpc[i - 1 - j];
-			lpc[i - 1 - j] += r * tmp;
+	int eff = max_order;
+	bool done = false;
+#pragma unroll
+	for(int i = 0; i < MO; i++) {
+		if(i < max_order && !done) {
+			double r = -ac[i + 1];
+#pragma unroll
+			for(int j = 0; j < MO; j++)
+				if(j < i) r -= lpc[j] * ac[i - j];
+			r /= err;
+			lpc[i] = r;
+#pragma unroll
+			for(int j = 0; j < MO / 2; j++)
+				if(j < (i >> 1)) {
+					const double tmp = lpc[j];
+					lpc[j] += r * lpc[i - 1 - j];
+					lpc[i - 1 - j] += r * tmp;
+				}
+			if(i & 1) lpc[i >> 1] += lpc[i >> 1] * r;
+			err *= (1.0 - r * r);
+			err_out[i] = err;
+			if(i + 1 == want_order) {
+#pragma unroll
+				for(int k = 0; k < MO; k++)
+					if(k <= i) coef_out[k] = (float)(-lpc[k]);
+			}
+			if(err == 0.0) { eff = i + 1; done = true; }
 		}
-		if(i & 1) lpc[j] += lpc[j] * r;
-		err *= (1.0 - r * r);
-		if(err_out) err_out[i] = err;
-		if(i + 1 == want_order)
-			for(int k = 0; k <= i; k++) coef_out[k] = (float)(-lpc[k]);
-		if(err == 0.0) return i + 1;
 	}
-	return max_order;
+	return eff;
 }
 
 // lpc.c:220-314 FLAC__lpc_quantize_coefficients
-__device__ int quantize_coefficients(const float *lp_coeff, int order, int precision, int *qlp, int *shift_out)
+template <int MO>
+__device__ __forceinline__ int quantize_coefficients(const float (&lp_coeff)[MO], int order, int precision, int (&qlp)[MO], int *shift_out)
 {
 	precision--;
 	int qmax = 1 << precision;
 	const int qmin = -qmax;
 	qmax--;
 	double cmax = 0.0;
-	for(int i = 0; i < order; i++) {
-		const double d = fabs((double)lp_coeff[i]);
-		if(d > cmax) cmax = d;
-	}
+#pragma unroll
+	for(int i = 0; i < MO; i++)
+		if(i < order) {
+			const double d = fabs((double)lp_coeff[i]);
+			if(d > cmax) cmax = d;
+		}
 	if(cmax <= 0.0) return 2;
 	int shift;
 	{
@@ -302,25 +321,29 @@ __device__ int quantize_coefficients(const float *lp_coeff, int order, int preci
 	double error = 0.0;
 	if(shift >= 0) {
 		const float scale = (float)(1 << shift);
-		for(int i = 0; i < order; i++) {
-			error += (double)__fmul_rn(lp_coeff[i], scale);
-			long long q = llround(error);
-			if(q > qmax) q = qmax;
-			else if(q < qmin) q = qmin;
-			error -= (double)q;
-			qlp[i] = (int)q;
-		}
+#pragma unroll
+		for(int i = 0; i < MO; i++)
+			if(i < order) {
+				error += (double)__fmul_rn(lp_coeff[i], scale);
+				long long q = llround(error);
+				if(q > qmax) q = qmax;
+				else if(q < qmin) q = qmin;
+				error -= (double)q;
+				qlp[i] = (int)q;
+			}
 	}
 	else {
 		const float scale = (float)(1 << (-shift));
-		for(int i = 0; i < order; i++) {
-			error += (double)__fdiv_rn(lp_coeff[i], scale);
-			long long q = llround(error);
-			if(q > qmax) q = qmax;
-			else if(q < qmin) q = qmin;
-			error -= (double)q;
-			qlp[i] = (int)q;
-		}
+#pragma unroll
+		for(int i = 0; i < MO; i++)
+			if(i < order) {
+				error += (double)__fdiv_rn(lp_coeff[i], scale);
+				long long q = llround(error);
+				if(q > qmax) q = qmax;
+				else if(q < qmin) q = qmin;
+				error -= (double)q;
+				qlp[i] = (int)q;
+			}
 		shift = 0;
 	}
 	*shift_out = shift;
@@ -328,8 +351,11 @@ __device__ int quantize_coefficients(const float *lp_coeff, int order, int preci
 }
 
 // One thread per (block, signal, window candidate). Writes nslots/nwin candidate slots.
+// autoc_unshifted: the autocorrelation was taken over the signal BEFORE its wasted bits were shifted out (k_autoc4 running
+// concurrently with k_meta): autoc(x >> w) = autoc(x) * 2^-2w exactly, applied here.
+template <int MO>
 __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ autoc, const DevCand *__restrict__ cands,
-                                            const SigMeta *__restrict__ meta, CandDesc *__restrict__ out, int nitems)
+                                            const SigMeta *__restrict__ meta, CandDesc *__restrict__ out, int nitems, int autoc_unshifted)
 {
 	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
 	if(gid >= nitems * P.nwin) return;
@@ -342,25 +368,30 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 
 	const int max_order = P.max_order;
 	const DevCand C = cands[win];
-	double ac[FB200_MAX_LPC_ORDER + 1];
+	double ac[MO + 1];
 	{
 		const double *a = autoc + ((size_t)C.sec * nitems + item) * P.lag_stride;
+		// 2^-2w (1.0 when nothing is to undo): an exact scaling of every sum
+		const double sc = autoc_unshifted ? __hiloint2double((1023 - 2 * meta[item].wasted) << 20, 0) : 1.0;
 		if(C.kind == 0) {
-			for(int l = 0; l <= max_order; l++) ac[l] = a[l];
+#pragma unroll
+			for(int l = 0; l <= MO; l++) ac[l] = l <= max_order ? a[l] * sc : 0.0;
 		}
 		else {
 			// punch-out = root - partial over max_order entries; entry [max_order] keeps the partial
 			// window's value (stream_encoder.c:4339-4340, 4370-4371).
 			const double *r = autoc + ((size_t)C.root * nitems + item) * P.lag_stride;
-			for(int l = 0; l < max_order; l++) ac[l] = r[l] - a[l];
-			ac[max_order] = a[max_order];
+#pragma unroll
+			for(int l = 0; l <= MO; l++) ac[l] = l < max_order ? r[l] * sc - a[l] * sc : (l == max_order ? a[l] * sc : 0.0);
 		}
 	}
 	if(ac[0] == 0.0) return;
 
-	double lpc_error[FB200_MAX_LPC_ORDER];
-	float coef[FB200_MAX_LPC_ORDER];
-	const int eff_max = levinson(ac, max_order, 0, lpc_error, coef);
+	double lpc_error[MO];
+	float coef[MO];
+#pragma unroll
+	for(int i = 0; i < MO; i++) { lpc_error[i] = 0.0; coef[i] = 0.0f; }
+	const int eff_max = levinson<MO>(ac, max_order, 0, lpc_error, coef);
 
 	int lo, hi;
 	if(P.exhaustive) { lo = 1; hi = eff_max; }
@@ -371,25 +402,37 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 		const double error_scale = 0.5 / (double)total_samples;
 		int best_index = 0;
 		double best_bits = (double)0xffffffffu;
-		for(int indx = 0, order = 1; indx < eff_max; indx++, order++) {
-			const double bits = expected_bits_scale(lpc_error[indx], error_scale) * (double)(total_samples - (uint32_t)order) + (double)((uint32_t)order * overhead);
-			if(bits < best_bits) { best_index = indx; best_bits = bits; }
-		}
+#pragma unroll
+		for(int indx = 0; indx < MO; indx++)
+			if(indx < eff_max) {
+				const uint32_t order = (uint32_t)indx + 1;
+				const double bits = expected_bits_scale(lpc_error[indx], error_scale) * (double)(total_samples - order) + (double)(order * overhead);
+				if(bits < best_bits) { best_index = indx; best_bits = bits; }
+			}
 		lo = hi = best_index + 1;
 	}
 	for(int order = lo; order <= hi; order++) {
 		CandDesc &D = slots[order - lo];
+		double err_o = 0.0;
+#pragma unroll
+		for(int i = 0; i < MO; i++)
+			if(i == order - 1) err_o = lpc_error[i];
 		// stream_encoder.c:4227-4229 "don't even try"
-		const double lbps = expected_bits_scale(lpc_error[order - 1], 0.5 / (double)(uint32_t)(P.bs - order));
+		const double lbps = expected_bits_scale(err_o, 0.5 / (double)(uint32_t)(P.bs - order));
 		if(lbps >= (double)sbps) continue;
 		int precision = P.qlp_precision;
 		if(sbps <= 17) precision = min(precision, 32 - sbps - (int)ilog2_u32((uint32_t)order));  // :4591-4595
-		(void)levinson(ac, order, order, nullptr, coef);
-		int q[FB200_MAX_LPC_ORDER], shift;
-		if(quantize_coefficients(coef, order, precision, q, &shift) != 0) continue;
+		double scratch_err[MO];
+		(void)levinson<MO>(ac, order, order, scratch_err, coef);
+		int q[MO], shift;
+#pragma unroll
+		for(int i = 0; i < MO; i++) q[i] = 0;
+		if(quantize_coefficients<MO>(coef, order, precision, q, &shift) != 0) continue;
 		// lpc.c:942-968
 		uint32_t abs_sum = 0;
-		for(int i = 0; i < order; i++) abs_sum += (uint32_t)abs(q[i]);
+#pragma unroll
+		for(int i = 0; i < MO; i++)
+			if(i < order) abs_sum += (uint32_t)abs(q[i]);
 		const uint64_t max_abs_sample = (uint64_t)1 << (sbps - 1);
 		const uint64_t max_pred = max_abs_sample * abs_sum;
 		const uint64_t max_pred_after = (uint64_t)(-1 * ((-1 * (int64_t)max_pred) >> shift));
@@ -398,7 +441,8 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 		D.order = order;
 		D.precision = precision;
 		D.shift = shift;
-		for(int i = 0; i < FB200_MAX_LPC_ORDER; i++) D.qlp[i] = (i < order) ? q[i] : 0;
+#pragma unroll
+		for(int i = 0; i < FB200_MAX_LPC_ORDER; i++) D.qlp[i] = (i < MO && i < order) ? q[i < MO ? i : 0] : 0;
 		D.valid = 1;
 	}
 }

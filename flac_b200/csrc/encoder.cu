@@ -80,7 +80,8 @@ struct fb200_encoder {
 	// stage-A outputs are double-buffered so that stage A (prep/autoc/lpc) of sub-batch i+1 can run on
 	// s_a concurrently with stage B (search/emit/scan/gather) of sub-batch i on the caller's stream
 	struct WS { int32_t *d_sig; SigMeta *d_meta; int *d_blkflags; double *d_autoc; CandDesc *d_cdesc; } ws[2] = {};
-	cudaStream_t s_a = nullptr;
+	cudaStream_t s_a = nullptr, s_meta = nullptr;
+	cudaEvent_t ev_meta_fork = nullptr, ev_meta_done = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
 	bool ev_b_valid[2] = {false, false};
 	// staging for the host entry point
@@ -99,6 +100,7 @@ struct fb200_encoder {
 	uint64_t launches = 0;
 	int host_chunks = 12;   // chunks per fb200_encode_host call (FB200_HOST_CHUNKS): copy/compute overlap granularity; measured best 8-12 (tools/sweep_host_chunks.py)
 	int pipe_chunks = 1;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS); see fb200_encode_device
+	int f64b = 0;         // FB200_SEARCH_F64B=1: the second warp of a signal runs on the FP64 pipe (measured SLOWER: -8 2.59 vs 2.02 ms; kept for A/B)
 	int debug_path = 0;   // FB200_DEBUG_PATH bit mask (bisecting aid): 1 = k_prep + k_autoc3 instead of k_meta + k_autoc4, 2 = general search, 4 = general emit
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
@@ -177,6 +179,14 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 	k.dis_const = c.disable_constant_subframes; k.dis_fixed = c.disable_fixed_subframes; k.dis_verb = c.disable_verbatim_subframes;
 	k.slot_stride = round_up((int)max_frame_bytes_for(c, (int)c.blocksize), 16);
 	k.slot_words = k.slot_stride / 4;
+	{
+		// k_emit3's frame buffer: a subframe is never longer than its verbatim form + n/2 + one bit per partition (the search
+		// keeps a candidate only if its estimate beats verbatim, and the Rice estimate undershoots by at most that); at most one
+		// of two channels is a side channel (bps + 1)
+		const size_t bits = 128 + (size_t)bs * ((size_t)c.bits_per_sample * c.channels + (c.channels == 2 ? 1 : 0)) + (size_t)c.channels * ((size_t)bs / 2 + 512 + 2 * c.bits_per_sample) + 16;
+		const int w = (int)((bits + 31) / 32) + 4;
+		k.emit3_words = w < k.slot_words ? w : k.slot_words;
+	}
 
 	std::vector<float> windows;
 	std::vector<DevSection> secs;
@@ -254,7 +264,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		}
 		// resident emit kernel: 1-2 channels, runs of R_T samples, one thread per run, at most 256 threads
 		if(g.fast_search3 && k.channels <= 2 && (bs / g.fast_search3) >= 32 && (bs / g.fast_search3) * k.channels <= 256 && ((size_t)bs * k.channels * 4) % 16 == 0) {
-			const size_t need = emit3_smem_bytes(bs, g.fast_search3, k.channels, k.slot_words);
+			const size_t need = emit3_smem_bytes(bs, g.fast_search3, k.channels, k.emit3_words);
 			if(need <= 200 * 1024) { g.emit3_rt = g.fast_search3; g.emit3_smem = need; }
 		}
 		g.raw_pipeline = g.emit3_rt != 0;
@@ -279,16 +289,26 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
 	const bool raw = g.raw_pipeline && !e->use_v1 && e->debug_path == 0 && ((uintptr_t)d_pcm & 15) == 0;
-	if(raw) launch_meta(k, d_pcm, e->d_meta, e->d_blkflags, nb, st);  // no planar copy: the fast kernels read the caller's PCM
+	// k_meta (HBM-bound) and k_autoc4 (FP64-bound) both only read the caller's PCM: they run concurrently on two streams when the
+	// autocorrelation does not need the meta data (it does under loose mid-side, to skip the inactive pair); k_lpc joins them
+	const bool overlap = raw && k.nwin > 0 && !k.loose_ms && !e->prof_on;
+	if(overlap) {
+		FB_CUDA(cudaEventRecord(e->ev_meta_fork, st));
+		FB_CUDA(cudaStreamWaitEvent(e->s_meta, e->ev_meta_fork, 0));
+		launch_meta(k, d_pcm, e->d_meta, e->d_blkflags, nb, e->s_meta);
+		FB_CUDA(cudaEventRecord(e->ev_meta_done, e->s_meta));
+	}
+	else if(raw) launch_meta(k, d_pcm, e->d_meta, e->d_blkflags, nb, st);  // no planar copy: the fast kernels read the caller's PCM
 	else launch_prep(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags, nb, st);
 	prof_mark(e, FB200_PROF_PREP, st);
 	e->launches++;
 	if(k.nwin > 0) {
-		if(raw) launch_autoc4(k, d_pcm, e->d_meta, g.d_secwin, bs_plus_slack(k.bs), g.d_secs, e->d_autoc, nitems, st);
+		if(raw) launch_autoc4(k, d_pcm, overlap ? nullptr : e->d_meta, g.d_secwin, bs_plus_slack(k.bs), g.d_secs, e->d_autoc, nitems, st);
 		else if(e->use_v1) launch_autoc_general(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		else launch_autoc3(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		prof_mark(e, FB200_PROF_AUTOC, st);
-		launch_lpc(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems, st);
+		if(overlap) FB_CUDA(cudaStreamWaitEvent(st, e->ev_meta_done, 0));
+		launch_lpc(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems, overlap ? 1 : 0, st);
 		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
@@ -304,6 +324,7 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	EncK k = g.k;
 	k.first_frame = first_frame;
 	k.blk0 = (uint32_t)frame_index0;
+	k.f64b = e->f64b;
 	k.file_blocks = (int)e->file_blocks;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
@@ -587,7 +608,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	ALLOC(e->d_ticket, sizeof(unsigned));
 	ALLOC(e->d_err, sizeof(int));
 #undef ALLOC
-	if(cudaStreamCreateWithFlags(&e->s_a, cudaStreamNonBlocking) != cudaSuccess ||
+	if(cudaStreamCreateWithFlags(&e->s_a, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&e->s_meta, cudaStreamNonBlocking) != cudaSuccess ||
+	   cudaEventCreateWithFlags(&e->ev_meta_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_meta_done, cudaEventDisableTiming) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_a[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_a[1], cudaEventDisableTiming) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_b[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_b[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -630,6 +652,8 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	{
 		const char *env = getenv("FB200_FORCE_GENERAL_KERNELS");
 		e->use_v1 = env && env[0] == '1';
+		const char *fb = getenv("FB200_SEARCH_F64B");
+		if(fb) e->f64b = atoi(fb) != 0;
 		const char *dp = getenv("FB200_DEBUG_PATH");
 		if(dp) e->debug_path = atoi(dp);
 		const char *hc = getenv("FB200_HOST_CHUNKS");
@@ -655,6 +679,9 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	}
 	if(e->ev_fork) cudaEventDestroy(e->ev_fork);
 	if(e->s_a) cudaStreamDestroy(e->s_a);
+	if(e->s_meta) cudaStreamDestroy(e->s_meta);
+	if(e->ev_meta_fork) cudaEventDestroy(e->ev_meta_fork);
+	if(e->ev_meta_done) cudaEventDestroy(e->ev_meta_done);
 	cudaFree(e->d_plans); cudaFree(e->d_slots); cudaFree(e->d_frame_bytes); cudaFree(e->d_chan_assign);
 	cudaFree(e->d_running); cudaFree(e->d_err);
 	cudaFree(e->d_crc_tab); cudaFree(e->d_lookback); cudaFree(e->d_ticket);

@@ -97,8 +97,10 @@ struct EncK {
 	int nsec, nwin, nslots;
 	int slot_stride;     // bytes per frame slot in the staging buffer (multiple of 16)
 	int slot_words;
+	int emit3_words;     // word-buffer capacity of k_emit3: the largest frame the search can produce (tighter than slot_words)
 	uint32_t first_frame;  // frame number of the call's first block
 	uint32_t blk0;         // index (inside the call) of this launch's first block
+	int f64b;            // k_search5: the second warp of a signal evaluates its candidates on the FP64 pipe
 	int file_blocks;     // > 0: frame numbers restart every file_blocks blocks (many-file batches: one stream per file, stream_encoder.c:3772)
 };
 
@@ -164,7 +166,7 @@ void launch_unpack(const void *packed, int bytes_per_sample, int32_t *pcm, unsig
 void launch_meta(const EncK &k, const int32_t *pcm, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
 void launch_prep(const EncK &k, const int32_t *pcm, int32_t *sig, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
 void launch_autoc_general(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
-void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, cudaStream_t st);
+void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, int autoc_unshifted, cudaStream_t st);
 void launch_search_general(const EncK &k, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st);
 void launch_emit_general(const EncK &k, size_t smem, const int32_t *sig, const int *blkflags, const SubframePlan *plans, uint8_t *slots, uint32_t *frame_bytes, uint32_t *chan_assign, int nb, cudaStream_t st);
 void launch_scan(const uint32_t *bytes, int n, unsigned long long *offsets, unsigned long long *running, cudaStream_t st);

@@ -38,10 +38,12 @@ void launch_autoc_general(const EncK &k, const int32_t *sig, const SigMeta *meta
 	else autoc_general<33>(k, sig, meta, windows, secs, autoc, nitems, st);
 }
 
-void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, cudaStream_t st)
+void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, int autoc_unshifted, cudaStream_t st)
 {
 	const int total = nitems * k.nwin;
-	k_lpc<<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems);
+	if(k.max_order <= 8) k_lpc<8><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems, autoc_unshifted);
+	else if(k.max_order <= 12) k_lpc<12><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems, autoc_unshifted);
+	else k_lpc<32><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems, autoc_unshifted);
 }
 
 void launch_search_general(const EncK &k, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st)

@@ -160,7 +160,7 @@ __host__ __device__ constexpr size_t search5_scratch_bytes(int max_po)
 __host__ __device__ constexpr size_t search5_smem_bytes(int bs, int R_T, int nsig, int wps, int max_po)
 {
 	return (size_t)nsig * (size_t)(kSearch4ZeroRow + (bs / R_T) * 36) * 4 + (size_t)nsig * wps * search5_scratch_bytes(max_po) +
-	       (size_t)nsig * (sizeof(SearchResult5) + 16) + 64;
+	       (size_t)nsig * (sizeof(SearchResult5) + 16) + 64 + (size_t)nsig * 48;
 }
 
 // One CTA per block. Shared memory: nsig signal slices (row layout: 36-word rows, a zero row in front), filled ONCE per
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 	SearchResult5 *const results = reinterpret_cast<SearchResult5 *>(after_scratch);
 	int *const queues = reinterpret_cast<int *>(after_scratch + (size_t)nsig * sizeof(SearchResult5));
 	uint64_t *const mbar = reinterpret_cast<uint64_t *>(queues + nsig + (nsig & 1));  // 8-byte aligned: nsig + pad ints after 16-byte aligned results
+	unsigned long long *const xch_all = reinterpret_cast<unsigned long long *>(mbar + 1);  // [nsig][6]: partial scan sums of a signal's second warp
 
 	const SigMeta *bm = meta + (size_t)blk * nsig;
 	const bool stereo_ms = (ch == 2 && nsig == 4);
@@ -306,13 +307,16 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 			// ---- residual pass, one predictor class per candidate
 			constexpr int NT12 = MAXORD < 12 ? MAXORD : 12;
 			bool bad = false;
-			if(!wide && narrow) {
+			// The second warp of a signal runs its candidates on the FP64 pipe even when 32-bit accumulation would do (exact: every
+			// value is an integer below 2^52): the IMAD pipe is half rate and the first warp keeps it busy, the DFMA pipe is idle
+			const bool via_f64 = wide || (WIDEK && WPS == 2 && part == 1 && P.f64b != 0);
+			if(!via_f64 && narrow) {
 				if(order <= 4) bad = fir_partition_sums<R_T, MAXORD, 4, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, leaf);
 				else if(order <= 8) bad = fir_partition_sums<R_T, MAXORD, 8, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, leaf);
 				else if(MAXORD > 8 && order <= 12) bad = fir_partition_sums<R_T, MAXORD, NT12, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, leaf);
 				else bad = fir_partition_sums<R_T, MAXORD, MAXORD, false, true>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, true, leaf);
 			}
-			else if(!wide) {
+			else if(!via_f64) {
 				if(order <= 8) bad = fir_partition_sums<R_T, MAXORD, 8, false, false>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, narrow, leaf);
 				else if(MAXORD > 8 && order <= 12) bad = fir_partition_sums<R_T, MAXORD, NT12, false, false>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, narrow, leaf);
 				else bad = fir_partition_sums<R_T, MAXORD, MAXORD, false, false>(xs, q, shift, order, 0, ntiles, lane, lpp_log, tpp, narrow, leaf);
@@ -437,8 +441,8 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 
 
 		if(bs > (int)kMaxFixedOrder) {
-			if(part == 0) {
-				// fixed-predictor scan (fixed.c:222-290) + constant detection over all tiles
+			if(part == 0 || WPS == 2) {
+				// fixed-predictor scan (fixed.c:222-290) + constant detection; the two warps of a signal take alternate tiles
 				unsigned long long te[5] = {0, 0, 0, 0, 0};
 				uint32_t diff = 0;
 				const int32_t x0 = xs[0];
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 				const bool lane_total_fits = (uint32_t)(sbps + 3) + ilog2_u32((uint32_t)(2 * (bs / 32) - 1)) <= 32u;
 				uint32_t t32[5] = {0, 0, 0, 0, 0};
 		#pragma unroll 1
-				for(int t = 0; t < ntiles; t++) {
+				for(int t = (WPS == 2 ? part : 0); t < ntiles; t += WPS) {
 					const int row = t * 32 + lane;
 					int xw[4 + R_T];
 					{
@@ -494,6 +498,26 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 		#pragma unroll
 				for(int k = 0; k < 5; k++) te[k] = warp_sum_u64(te[k]);
 				eq = warp_and(eq);
+				if(WPS == 2) {
+					// the second warp hands its partial sums to the first through shared memory (named barrier: 64 threads of the signal)
+					unsigned long long *xch = xch_all + 6 * sidx;
+					if(part == 1) {
+						if(lane == 0) {
+#pragma unroll
+							for(int k = 0; k < 5; k++) xch[k] = te[k];
+							xch[5] = eq;
+						}
+						__threadfence_block();
+						asm volatile("bar.arrive %0, 64;" ::"r"(1 + sidx) : "memory");
+					}
+					else {
+						asm volatile("bar.sync %0, 64;" ::"r"(1 + sidx) : "memory");
+#pragma unroll
+						for(int k = 0; k < 5; k++) te[k] += xch[k];
+						eq &= (uint32_t)xch[5];
+					}
+				}
+				if(part == 0) {
 				int guess;
 				{
 					const unsigned long long m34 = te[3] < te[4] ? te[3] : te[4], m234 = te[2] < m34 ? te[2] : m34, m1234 = te[1] < m234 ? te[1] : m234;
@@ -532,6 +556,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 						evaluate(fo, SF_FIXED, fo, 0, 0, 0, 0, q);
 					}
 				}
+				}  // part == 0
 			}
 			if(P.max_order > 0 && !is_constant) {
 				// LPC candidates: a queue per signal; a constant signal's LPC results (second warp) are dropped at the merge

@@ -297,7 +297,9 @@ struct FLAC__StreamEncoderPrivate {
 	fb200_encoder *gpu;
 	fb200_decoder *vdec;
 	uint32_t batch;
-	std::vector<int32_t> pending;  // interleaved
+	std::vector<int32_t> pending;  // interleaved (kept for --verify)
+	std::vector<uint8_t> pending_packed;  // the same samples as little-endian 2-/3-byte PCM: what crosses PCIe (fb200_encode_host_packed)
+	uint32_t pack_bytes;           // 2 (bps <= 16), 3 (bps <= 24)
 	uint64_t pending_samples;
 	std::vector<uint8_t> frames;
 	std::vector<uint64_t> offsets;
@@ -338,6 +340,7 @@ static void enc_release(FLAC__StreamEncoder *e)
 	if(q->file && q->owns_file) fclose(q->file);
 	q->file = nullptr;
 	q->pending.clear(); q->pending.shrink_to_fit();
+	q->pending_packed.clear(); q->pending_packed.shrink_to_fit();
 	q->frames.clear(); q->frames.shrink_to_fit();
 	q->offsets.clear(); q->verify_pcm.clear();
 	q->pending_samples = 0;
@@ -543,7 +546,8 @@ static bool enc_flush(FLAC__StreamEncoder *e)
 	if(q->frames.size() < cap) q->frames.resize(cap);
 	if(q->offsets.size() < nfr + 1) q->offsets.resize(nfr + 1);
 	uint32_t nframes = 0;
-	if(fb200_encode_host(q->gpu, q->pending.data(), q->pending_samples, q->frames_written, q->frames.data(), q->frames.size(), q->offsets.data(), &nframes) != FB200_OK) {
+	// the batch goes to the device as packed 16-/24-bit PCM (half / three quarters of the int32 traffic), widened there
+	if(fb200_encode_host_packed(q->gpu, q->pending_packed.data(), q->pack_bytes, q->pending_samples, q->frames_written, q->frames.data(), q->frames.size(), q->offsets.data(), &nframes) != FB200_OK) {
 		e->protected_->state = FLAC__STREAM_ENCODER_FRAMING_ERROR;
 		return false;
 	}
@@ -632,7 +636,9 @@ static FLAC__StreamEncoderInitStatus enc_init_common(FLAC__StreamEncoder *e, boo
 		fb200_decoder_config dc = {c.channels, c.bits_per_sample, c.sample_rate, c.blocksize};
 		if(fb200_decoder_create(&dc, 0, q->batch, &q->vdec) != FB200_OK) { enc_release(e); return FLAC__STREAM_ENCODER_INIT_STATUS_ENCODER_ERROR; }
 	}
-	q->pending.resize((size_t)q->batch * c.blocksize * c.channels);
+	q->pending.resize(p->verify ? (size_t)q->batch * c.blocksize * c.channels : 0);
+	q->pack_bytes = c.bits_per_sample <= 16 ? 2 : 3;
+	q->pending_packed.resize((size_t)q->batch * c.blocksize * c.channels * q->pack_bytes);
 	q->pending_samples = 0;
 	q->md5.init();
 	q->frames_written = 0; q->samples_written = 0; q->bytes_written = 0; q->first_seekpoint_to_check = 0;
@@ -732,9 +738,22 @@ FLAC__bool FLAC__stream_encoder_process_interleaved(FLAC__StreamEncoder *e, cons
 	while(done < samples) {
 		const uint32_t n = (uint32_t)std::min<uint64_t>(samples - done, cap - q->pending_samples);
 		const FLAC__int32 *src = buffer + (size_t)done * ch;
-		for(size_t i = 0; i < (size_t)n * ch; i++)
-			if(src[i] < smin || src[i] > smax) { p->state = FLAC__STREAM_ENCODER_CLIENT_ERROR; return false; }  // stream_encoder.c:2586-2596
-		memcpy(q->pending.data() + (size_t)q->pending_samples * ch, src, (size_t)n * ch * sizeof(FLAC__int32));
+		uint8_t *pk = q->pending_packed.data() + (size_t)q->pending_samples * ch * q->pack_bytes;
+		if(q->pack_bytes == 2) {
+			for(size_t i = 0; i < (size_t)n * ch; i++) {
+				const FLAC__int32 v = src[i];
+				if(v < smin || v > smax) { p->state = FLAC__STREAM_ENCODER_CLIENT_ERROR; return false; }  // stream_encoder.c:2586-2596
+				pk[2 * i] = (uint8_t)v; pk[2 * i + 1] = (uint8_t)(v >> 8);
+			}
+		}
+		else {
+			for(size_t i = 0; i < (size_t)n * ch; i++) {
+				const FLAC__int32 v = src[i];
+				if(v < smin || v > smax) { p->state = FLAC__STREAM_ENCODER_CLIENT_ERROR; return false; }
+				pk[3 * i] = (uint8_t)v; pk[3 * i + 1] = (uint8_t)(v >> 8); pk[3 * i + 2] = (uint8_t)(v >> 16);
+			}
+		}
+		if(p->verify) memcpy(q->pending.data() + (size_t)q->pending_samples * ch, src, (size_t)n * ch * sizeof(FLAC__int32));
 		if(p->do_md5) q->md5.update_samples(src, (size_t)n * ch, (bps + 7) / 8);
 		q->pending_samples += n;
 		done += n;
@@ -865,6 +884,11 @@ struct FLAC__StreamDecoderPrivate {
 	size_t batch_first, batch_count;
 	std::vector<int32_t> pcm;
 	std::vector<uint64_t> offs;
+	std::vector<uint32_t> batch_status, batch_bytes;       // per frame of the decoded batch
+	std::vector<fb200_subframe_info> batch_sub;           // per (frame, channel) of the decoded batch
+	std::vector<int32_t> residual;                        // scratch: residuals of the frame being delivered (FLAC__Subframe.residual)
+	uint64_t expect_pos;          // byte offset (in `audio`) where the next frame should start
+	bool lost_sync_reported;
 	std::vector<int32_t> planar;
 	MD5 md5;
 	uint64_t samples_decoded;
@@ -961,48 +985,42 @@ static uint32_t parse_frame_header(const uint8_t *p, size_t avail, const FLAC__S
 	return (uint32_t)pos + 1;
 }
 
-// locate frame boundaries: a frame ends where the running CRC-16 (over frame bytes incl. footer) is zero
-// and either the data ends or a valid frame header follows.
-static void dec_build_index(FLAC__StreamDecoder *d)
+// Frame index = the GPU front end's candidates (sync code + self-consistent header incl. CRC-8 at every byte position of the
+// stream at once: fb200_decoder_index_host), kept when the header agrees with STREAMINFO. A candidate's END is not known
+// here -- frames carry no length field -- and is not needed: the batch decode bounds every frame by the largest legal frame,
+// finds its true length by parsing it and checks the CRC-16 over exactly that (fb200_decode_indexed_host). Junk between or
+// after frames (ID3v1 / APE tags, padding) therefore costs nothing, and a corrupt frame loses only itself.
+static bool dec_build_index(FLAC__StreamDecoder *d)
 {
 	FLAC__StreamDecoderPrivate *q = d->private_;
 	const uint8_t *a = q->audio.data();
 	const size_t n = q->audio.size() - 64;  // slack at the end
-	size_t pos = 0;
+	std::vector<uint64_t> cand;
+	uint32_t ncand = 0;
+	size_t cap = std::max<size_t>(1 << 16, n / 256);
+	for(;;) {
+		cand.resize(cap);
+		const int rc = fb200_decoder_index_host(q->gpu, a, n, cand.data(), (uint32_t)std::min<size_t>(cap, 0xffffffffu), &ncand);
+		if(rc == FB200_OK) break;
+		if(rc != FB200_ERR_OUTPUT_TOO_SMALL || cap >= n) return false;
+		cap = std::min(n, cap * 8);
+	}
 	uint64_t sample = 0;
-	bool reported = false;
-	while(pos + 6 <= n) {
+	const bool fixed_bs = q->si.min_blocksize == q->si.max_blocksize && q->si.max_blocksize;
+	for(uint32_t i = 0; i < ncand; i++) {
 		FrameIndexEntry fe;
 		memset(&fe, 0, sizeof fe);
-		const uint32_t hl = parse_frame_header(a + pos, n - pos, q->si, fe);
-		if(!hl) {
-			if(!reported && q->error_cb) { q->error_cb(d, FLAC__STREAM_DECODER_ERROR_STATUS_LOST_SYNC, q->client_data); reported = true; }
-			pos++;
-			continue;
-		}
-		uint16_t crc = 0;
-		size_t end = 0;
-		for(size_t i = pos; i < n; i++) {
-			crc = (uint16_t)((crc << 8) ^ g_crc16[(crc >> 8) ^ a[i]]);
-			const size_t e = i + 1;
-			if(crc == 0 && e - pos >= hl + 3) {
-				FrameIndexEntry nx;
-				if(e == n || parse_frame_header(a + e, n - e, q->si, nx)) { end = e; break; }
-			}
-		}
-		if(!end) {
-			if(q->error_cb) q->error_cb(d, FLAC__STREAM_DECODER_ERROR_STATUS_FRAME_CRC_MISMATCH, q->client_data);
-			pos++;
-			continue;
-		}
-		reported = false;
-		fe.offset = pos; fe.length = (uint32_t)(end - pos);
+		const size_t pos = (size_t)cand[i];
+		if(!parse_frame_header(a + pos, n - pos, q->si, fe)) continue;
+		if(fe.channels != q->si.channels || fe.bps != q->si.bits_per_sample || fe.blocksize > (q->si.max_blocksize ? q->si.max_blocksize : 65535u)) continue;
+		fe.offset = pos; fe.length = 0;
 		q->index.push_back(fe);
-		q->first_sample.push_back(fe.variable ? fe.number : sample);
-		sample = q->first_sample.back() + fe.blocksize;
-		pos = end;
+		const uint64_t fs = fe.variable ? fe.number : (fixed_bs ? fe.number * q->si.max_blocksize : sample);
+		q->first_sample.push_back(fs);
+		sample = fs + fe.blocksize;
 	}
 	q->indexed = true;
+	return true;
 }
 
 static bool dec_read_metadata(FLAC__StreamDecoder *d)
@@ -1120,7 +1138,6 @@ static bool dec_prepare_audio(FLAC__StreamDecoder *d)
 	q->audio.assign(q->in.begin() + (long)q->in_pos, q->in.end());
 	q->audio.resize(q->audio.size() + 64, 0);
 	q->in.clear(); q->in.shrink_to_fit(); q->in_pos = 0;
-	dec_build_index(d);
 	const uint32_t bs = q->si.max_blocksize ? q->si.max_blocksize : 4096;
 	if(q->si.bits_per_sample > 24) {
 		if(q->error_cb) q->error_cb(d, FLAC__STREAM_DECODER_ERROR_STATUS_UNPARSEABLE_STREAM, q->client_data);
@@ -1132,60 +1149,72 @@ static bool dec_prepare_audio(FLAC__StreamDecoder *d)
 		d->protected_->state = FLAC__STREAM_DECODER_MEMORY_ALLOCATION_ERROR;
 		return false;
 	}
+	fb200_decoder_enable_subframe_info(q->gpu, 1);
+	if(!dec_build_index(d)) {
+		d->protected_->state = FLAC__STREAM_DECODER_MEMORY_ALLOCATION_ERROR;
+		return false;
+	}
+	q->expect_pos = 0; q->lost_sync_reported = false;
 	q->md5.init();
 	return true;
 }
 
-// decode the batch that contains frame `first`
+// decode the batch that starts at index entry `first`
 static bool dec_decode_batch(FLAC__StreamDecoder *d, size_t first)
 {
 	FLAC__StreamDecoderPrivate *q = d->private_;
 	const size_t count = std::min<size_t>(batch_blocks(), q->index.size() - first);
 	const uint32_t bs = q->si.max_blocksize ? q->si.max_blocksize : 4096, ch = q->si.channels;
-	q->offs.resize(count + 1);
-	// frames of a batch are contiguous in `audio` unless junk lies between them; gather offsets relative to the first
-	const uint64_t base = q->index[first].offset;
-	bool contiguous = true;
-	for(size_t i = 0; i < count; i++) {
-		q->offs[i] = q->index[first + i].offset - base;
-		if(i && q->index[first + i].offset != q->index[first + i - 1].offset + q->index[first + i - 1].length) contiguous = false;
-	}
-	q->offs[count] = q->index[first + count - 1].offset + q->index[first + count - 1].length - base;
-	std::vector<uint8_t> packed;
-	const uint8_t *src = q->audio.data() + base;
-	if(!contiguous) {
-		uint64_t o = 0;
-		for(size_t i = 0; i < count; i++) {
-			const FrameIndexEntry &fe = q->index[first + i];
-			packed.insert(packed.end(), q->audio.begin() + (long)fe.offset, q->audio.begin() + (long)(fe.offset + fe.length));
-			q->offs[i] = o; o += fe.length;
-		}
-		q->offs[count] = o;
-		packed.resize(packed.size() + 64, 0);
-		src = packed.data();
-	}
+	q->offs.resize(count);
+	for(size_t i = 0; i < count; i++) q->offs[i] = q->index[first + i].offset;
+	// how far a frame may reach: twice the verbatim worst case (STREAMINFO's max_framesize is advisory and may be absent);
+	// the bound only limits how far a broken parse can run, the true length comes out of the parse
+	const uint32_t max_fb = 64 + 2 * ch * (uint32_t)(((uint64_t)bs * (q->si.bits_per_sample + 2) + 7) / 8 + 64);
 	q->pcm.resize(count * (size_t)bs * ch);
-	uint64_t ns = 0;
-	uint32_t bad = 0;
-	if(fb200_decode_host(q->gpu, src, q->offs.data(), (uint32_t)count, q->pcm.data(), (uint64_t)count * bs, &ns, &bad) != FB200_OK) {
+	q->batch_status.resize(count); q->batch_bytes.resize(count); q->batch_sub.resize(count * (size_t)ch);
+	if(fb200_decode_indexed_host(q->gpu, q->offs.data(), (uint32_t)count, max_fb, q->audio.size() - 64, q->pcm.data(), (uint64_t)count * bs,
+	                             q->batch_status.data(), q->batch_bytes.data()) != FB200_OK ||
+	   fb200_decoder_get_subframe_info(q->gpu, q->batch_sub.data(), (uint32_t)count) != FB200_OK) {
 		d->protected_->state = FLAC__STREAM_DECODER_ABORTED;
 		return false;
 	}
-	if(bad && q->error_cb) q->error_cb(d, FLAC__STREAM_DECODER_ERROR_STATUS_FRAME_CRC_MISMATCH, q->client_data);
 	q->batch_first = first; q->batch_count = count;
 	return true;
 }
 
-// hand one frame to the client (write_audio_frame_to_client_, stream_decoder.c:3578-3635)
+// hand one frame to the client (write_audio_frame_to_client_, stream_decoder.c:3578-3635); frames that fail are reported
+// through the error callback and NOT delivered, like the reference (stream_decoder.c:2443-2590)
 static bool dec_deliver_next(FLAC__StreamDecoder *d)
 {
 	FLAC__StreamDecoderPrivate *q = d->private_;
-	if(q->next_frame >= q->index.size()) { d->protected_->state = FLAC__STREAM_DECODER_END_OF_STREAM; return true; }
-	if(q->batch_count == 0 || q->next_frame < q->batch_first || q->next_frame >= q->batch_first + q->batch_count)
-		if(!dec_decode_batch(d, q->next_frame)) return false;
+	for(;;) {
+		if(q->next_frame >= q->index.size()) { d->protected_->state = FLAC__STREAM_DECODER_END_OF_STREAM; return true; }
+		if(q->batch_count == 0 || q->next_frame < q->batch_first || q->next_frame >= q->batch_first + q->batch_count)
+			if(!dec_decode_batch(d, q->next_frame)) return false;
+		const size_t bi = q->next_frame - q->batch_first;
+		const FrameIndexEntry &fe = q->index[q->next_frame];
+		const uint32_t st = q->batch_status[bi] & 0xffu;
+		if(fe.offset < q->expect_pos && !q->did_seek) { q->next_frame++; continue; }  // a header look-alike inside the previous frame
+		if(st != 0) {
+			// a broken frame (or a look-alike in junk): report once per damaged stretch, move on to the next candidate
+			if(q->error_cb) {
+				const FLAC__StreamDecoderErrorStatus es = st == 7 ? FLAC__STREAM_DECODER_ERROR_STATUS_FRAME_CRC_MISMATCH :
+				    (st == 2 || st == 3) ? FLAC__STREAM_DECODER_ERROR_STATUS_BAD_HEADER :
+				    st == 4 ? FLAC__STREAM_DECODER_ERROR_STATUS_UNPARSEABLE_STREAM : FLAC__STREAM_DECODER_ERROR_STATUS_LOST_SYNC;
+				q->error_cb(d, es, q->client_data);
+			}
+			q->next_frame++;
+			continue;
+		}
+		if(fe.offset > q->expect_pos && !q->did_seek && q->expect_pos != 0 && q->error_cb)
+			q->error_cb(d, FLAC__STREAM_DECODER_ERROR_STATUS_LOST_SYNC, q->client_data);  // junk between two frames
+		q->expect_pos = fe.offset + q->batch_bytes[bi];
+		break;
+	}
+	const size_t bi = q->next_frame - q->batch_first;
 	const FrameIndexEntry &fe = q->index[q->next_frame];
 	const uint32_t bsmax = q->si.max_blocksize ? q->si.max_blocksize : 4096, ch = q->si.channels;
-	const int32_t *src = q->pcm.data() + (q->next_frame - q->batch_first) * (size_t)bsmax * ch;
+	const int32_t *src = q->pcm.data() + bi * (size_t)bsmax * ch;
 	uint32_t bs = fe.blocksize;
 	uint64_t first_sample = q->first_sample[q->next_frame];
 	uint32_t skip = 0;
@@ -1208,6 +1237,35 @@ static bool dec_deliver_next(FLAC__StreamDecoder *d)
 	fr.header.number_type = FLAC__FRAME_NUMBER_TYPE_SAMPLE_NUMBER;  // the reference always hands out sample numbers (:2936-2944)
 	fr.header.number.sample_number = first_sample + skip;
 	fr.header.crc = fe.crc8;
+	{   // FLAC__Frame.subframes[] (format.h:211-484; consumer: src/flac/analyze.c) from what the decode kernels parsed;
+		// the CRC-16 footer from the frame's last two bytes
+		const uint8_t *fb = q->audio.data() + fe.offset;
+		const uint32_t flen = q->batch_bytes[bi];
+		if(flen >= 2) fr.footer.crc = (FLAC__uint16)((fb[flen - 2] << 8) | fb[flen - 1]);
+		for(uint32_t c = 0; c < ch; c++) {
+			const fb200_subframe_info &I = q->batch_sub[bi * ch + c];
+			FLAC__Subframe &sf = fr.subframes[c];
+			sf.wasted_bits = I.wasted_bits;
+			switch(I.type) {
+				case 0: sf.type = FLAC__SUBFRAME_TYPE_CONSTANT; sf.data.constant.value = I.warmup[0]; break;
+				case 1: sf.type = FLAC__SUBFRAME_TYPE_VERBATIM; sf.data.verbatim.data.int32 = nullptr; sf.data.verbatim.data_type = FLAC__VERBATIM_SUBFRAME_DATA_TYPE_INT32; break;
+				case 2:
+					sf.type = FLAC__SUBFRAME_TYPE_FIXED;
+					sf.data.fixed.order = I.order;
+					sf.data.fixed.entropy_coding_method.type = (FLAC__EntropyCodingMethodType)I.entropy_method;
+					sf.data.fixed.entropy_coding_method.data.partitioned_rice.order = I.partition_order;
+					for(uint32_t k = 0; k < I.order && k < 4; k++) sf.data.fixed.warmup[k] = I.warmup[k];
+					break;
+				default:
+					sf.type = FLAC__SUBFRAME_TYPE_LPC;
+					sf.data.lpc.order = I.order; sf.data.lpc.qlp_coeff_precision = I.qlp_coeff_precision; sf.data.lpc.quantization_level = I.quantization_level;
+					sf.data.lpc.entropy_coding_method.type = (FLAC__EntropyCodingMethodType)I.entropy_method;
+					sf.data.lpc.entropy_coding_method.data.partitioned_rice.order = I.partition_order;
+					for(uint32_t k = 0; k < I.order; k++) { sf.data.lpc.qlp_coeff[k] = I.qlp_coeff[k]; sf.data.lpc.warmup[k] = I.warmup[k]; }
+					break;
+			}
+		}
+	}
 	d->protected_->channels = ch; d->protected_->bits_per_sample = fe.bps; d->protected_->sample_rate = fe.sample_rate;
 	d->protected_->blocksize = bs - skip; d->protected_->channel_assignment = fr.header.channel_assignment;
 	if(d->protected_->md5_checking && !q->did_seek) q->md5.update_samples(src, (size_t)bs * ch, (fe.bps + 7) / 8);
@@ -1382,7 +1440,7 @@ FLAC__bool FLAC__stream_decoder_reset(FLAC__StreamDecoder *d)
 {
 	if(DEC_UNINIT(d)) return false;
 	FLAC__StreamDecoderPrivate *q = d->private_;
-	if(q->indexed) { q->next_frame = 0; q->skip_samples = 0; q->batch_count = 0; q->did_seek = false; q->md5.init(); d->protected_->state = FLAC__STREAM_DECODER_SEARCH_FOR_FRAME_SYNC; return true; }
+	if(q->indexed) { q->next_frame = 0; q->skip_samples = 0; q->batch_count = 0; q->did_seek = false; q->expect_pos = 0; q->md5.init(); d->protected_->state = FLAC__STREAM_DECODER_SEARCH_FOR_FRAME_SYNC; return true; }
 	return !q->metadata_done && q->in.empty();
 }
 

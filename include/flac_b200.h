@@ -194,12 +194,45 @@ int fb200_decode_host(fb200_decoder *dec, const uint8_t *frames, const uint64_t 
                       uint32_t *bad_frames);
 
 /* _device: d_frames must be readable 8 bytes past the last frame (the bit reader fetches whole
- * words); d_frame_status[i] = status (low byte, 0 = ok) | decoded blocksize << 8. */
+ * aligned words); d_frame_status[i] = status (low byte, 0 = ok) | decoded blocksize << 8. */
 int fb200_decode_device(fb200_decoder *dec, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,
                         int32_t *d_pcm_interleaved, uint64_t pcm_capacity_samples, uint32_t *d_frame_status,
                         void *cuda_stream, int sync);
 
 uint64_t fb200_decoder_launch_count(const fb200_decoder *dec);
+
+/* Per-frame status words of the last fb200_decode_host / fb200_decode_indexed_host call: low byte 0 = ok, else
+ * 1 sync, 2 header, 3 CRC-8, 4 unsupported, 5 parse / sample out of range, 6 length, 7 CRC-16, 8 STREAMINFO mismatch;
+ * upper 24 bits: the frame's blocksize. (The reference reports these per frame through its error callback and does not
+ * deliver the frame: stream_decoder.c:2443-2590.) */
+int fb200_decoder_get_frame_status(const fb200_decoder *dec, uint32_t *status, uint32_t nframes);
+
+/* What the reference hands a client in FLAC__Frame.subframes[] (include/FLAC/format.h:211-484; consumer: src/flac/analyze.c),
+ * collected by the decode kernels when enabled: one record per (frame, channel) of the last decode call. */
+typedef struct {
+	uint8_t type;       /* 0 constant, 1 verbatim, 2 fixed, 3 lpc */
+	uint8_t order;
+	uint8_t wasted_bits;
+	uint8_t qlp_coeff_precision;
+	int8_t quantization_level;
+	uint8_t entropy_method;   /* 0 PARTITIONED_RICE, 1 PARTITIONED_RICE2 */
+	uint8_t partition_order;
+	uint8_t reserved;
+	int32_t qlp_coeff[FB200_MAX_LPC_ORDER];
+	int32_t warmup[FB200_MAX_LPC_ORDER];  /* constant subframes: warmup[0] is the value */
+} fb200_subframe_info;
+int fb200_decoder_enable_subframe_info(fb200_decoder *dec, int on);
+int fb200_decoder_get_subframe_info(fb200_decoder *dec, fb200_subframe_info *info, uint32_t nframes);
+
+/* Stream-level front end: fb200_decoder_index_host copies `stream` (frames only or a whole .flac file) to the device and
+ * returns, ascending, every byte offset that carries a sync code and a self-consistent frame header (frame_sync_ +
+ * read_frame_header_ incl. CRC-8, stream_decoder.c:2321-2371, 2624-2947, for all positions at once). The stream stays
+ * resident; fb200_decode_indexed_host decodes the frames STARTING at begins[i], each bounded by max_frame_bytes: the parse
+ * finds the frame's true length (frame_bytes[i]) and the CRC-16 is checked over exactly that, so junk between or after frames
+ * (ID3v1 / APE tags, padding) costs nothing. A false candidate fails its parse or CRC-16 (frame_status[i] != 0). */
+int fb200_decoder_index_host(fb200_decoder *dec, const uint8_t *stream, uint64_t nbytes, uint64_t *candidates, uint32_t capacity, uint32_t *ncandidates);
+int fb200_decode_indexed_host(fb200_decoder *dec, const uint64_t *begins, uint32_t nframes, uint32_t max_frame_bytes, uint64_t stream_bytes,
+                              int32_t *pcm_interleaved, uint64_t pcm_capacity_samples, uint32_t *frame_status, uint32_t *frame_bytes);
 
 enum { FB200_DPROF_WALK = 0, FB200_DPROF_CRC, FB200_DPROF_FRAMES, FB200_DPROF_KERNELS };  /* k_dec_walk, k_dec_crc, k_dec_frames */
 int fb200_decoder_set_profiling(fb200_decoder *dec, int on);

@@ -181,3 +181,80 @@ def test_encode_decode_round_trip_full_size():
     y = dec.decode(stream, offs)
     dec.close()
     assert y.shape == x.shape and np.array_equal(x, y)
+
+
+def test_gpu_front_end_index_with_junk_around_frames():
+    """fb200_decoder_index_host + fb200_decode_indexed_host: frames are found with no caller-supplied offsets, junk in front of,
+    between and behind them (ID3v1-style tag) costs nothing, every frame's true length comes out of the parse."""
+    import flac_b200
+    x = signals.music_like(4096 * 6 + 1000, 2, 16, 44100, seed=13)
+    frames = _encoded_frames(x, 16, 44100, 8)
+    junk0, junk1, tag = b"\x00\x01\x02" * 11, b"\xff\xf8junk-that-looks-like-sync\xff\xf9" * 3, b"TAG" + b"\x55" * 125
+    blob, starts = bytearray(junk0), []
+    for i, f in enumerate(frames):
+        starts.append(len(blob))
+        blob += f
+        if i == 2:
+            blob += junk1
+    blob += tag
+    dec = flac_b200.Decoder(2, 16, 44100, 4096)
+    try:
+        cand = dec.index(np.frombuffer(bytes(blob), dtype=np.uint8))
+        assert set(starts) <= set(int(c) for c in cand), "a true frame start is missing from the candidates"
+        pcm, st, fb = dec.decode_indexed(cand, 2 * 4096 * 2 * 3)
+        good = {int(c): i for i, c in enumerate(cand) if (st[i] & 0xff) == 0}
+        assert sorted(good) == starts, f"accepted {sorted(good)} expected {starts}"
+        y = np.concatenate([pcm[good[s] * 4096: good[s] * 4096 + (int(st[good[s]]) >> 8)] for s in starts])
+        assert np.array_equal(y, x)
+        assert [int(fb[good[s]]) for s in starts] == [len(f) for f in frames]
+    finally:
+        dec.close()
+
+
+def test_subframe_info_matches_the_encoders_plan():
+    """FLAC__Frame.subframes[] material: type / order / precision / shift / partition order / coefficients / warm-up reported by the
+    decode kernels equal what the encoder decided (its plans) for every subframe of every frame."""
+    import flac_b200
+    x = signals.music_like(4096 * 4, 2, 16, 44100, seed=31)
+    enc = flac_b200.Encoder(flac_b200.preset(2, 16, 44100, 8))
+    stream, offs = enc.encode(x)
+    plans, ca = enc.debug_plans(4)
+    enc.close()
+    dec = flac_b200.Decoder(2, 16, 44100, 4096)
+    try:
+        dec.enable_subframe_info(True)
+        y = dec.decode(stream, offs)
+        assert np.array_equal(x, y)
+        info = dec.subframe_info(4)
+        for f in range(4):
+            a = int(ca[f])
+            sel = [(0 if a in (0, 1) else (3 if a == 2 else 2)), (1 if a in (0, 2) else 3)]
+            for c in range(2):
+                p, i = plans[f * 4 + sel[c]], info[f * 2 + c]
+                want_type = {0: 0, 1: 1, 2: 2, 3: 3}[p.type]
+                assert i.type == want_type and i.wasted_bits == p.wasted
+                if p.type >= 2:
+                    assert i.order == p.order and i.partition_order == p.porder and i.entropy_method == p.method
+                if p.type == 3:
+                    assert i.qlp_coeff_precision == p.precision and i.quantization_level == p.shift
+                    assert list(i.qlp_coeff[:p.order]) == list(p.qlp[:p.order])
+    finally:
+        dec.close()
+
+
+def test_truncated_and_lying_frames_never_read_past_their_end():
+    """A frame whose header claims more data than the buffer holds (valid CRC-8, truncated body) is reported, not decoded;
+    the neighbours decode. (Bit reader returns zeros past the frame end: no out-of-bounds read.)"""
+    import flac_b200
+    x = signals.music_like(4096 * 3, 2, 16, 44100, seed=23)
+    frames = _encoded_frames(x, 16, 44100, 5)
+    cut = frames[1][: len(frames[1]) // 3]
+    stream, offs = _offsets([frames[0], cut, frames[2]])
+    dec = flac_b200.Decoder(2, 16, 44100, 4096)
+    try:
+        with pytest.raises(flac_b200.FlacB200Error):
+            dec.decode(stream, offs)
+        st = dec.frame_status(3)
+        assert (st[0] & 0xff) == 0 and (st[1] & 0xff) != 0 and (st[2] & 0xff) == 0
+    finally:
+        dec.close()

@@ -3,7 +3,7 @@
 TAG=${1:-r2}; shift
 mkdir -p gpurun_out
 for W in "$@"; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_emit3|k_search|k_autoc3|k_prep|k_lpc|k_meta|k_unpack|k_dec" --launch-skip ${SKIP:-15} --launch-count ${COUNT:-5} \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-k_}" --launch-skip ${SKIP:-15} --launch-count ${COUNT:-5} \
      -f -o gpurun_out/${TAG}_${W} python bench.py --workload $W --kernels-only --steps 1 --warmup 3 > gpurun_out/${TAG}_${W}_ncu.log 2>&1
   echo "ncu $W rc=$?"
 done
