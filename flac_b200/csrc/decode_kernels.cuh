@@ -65,58 +65,37 @@ struct DecSubframeInfo {
 	int32_t warmup[FB200_MAX_LPC_ORDER];  // warm-up samples (constant: [0] = the value)
 };
 
-// MSB-first bit reader over global memory: a 64-bit left-aligned accumulator (at least 32 valid bits after every refill) and
-// ONE word of look-ahead in a register. A lane walks its own frame, so nothing but the reader itself can hide its load
-// latency: the word that enters the accumulator was loaded one refill earlier (covers the L1 latency), and whenever the
-// reader enters a new 128-byte line it prefetches the line two ahead into L1 (covers L2 / DRAM). The refill is branch-free
-// (predicated), so lanes at different bit positions stay converged. Words past `nwords` read as zeros: no read leaves the
-// frame's last 16-byte granule. (First version: one dependent 32-bit load per refill = ~250 cycles per Rice code; second: a
-// three-deep queue of 128-bit loads whose clamping touched the data at once and whose rotation cost 5 moves per word.)
+// MSB-first bit reader over global memory. The reader holds the two words the current position straddles (w0, w1: one funnel
+// shift yields the next 32 bits at any bit position) and TWO words of look-ahead (w2, w3) that were loaded one and two word
+// crossings earlier. A lane walks its own frame, so nothing but the reader itself can hide its load latency: two crossings
+// (~5 Rice codes of the whole warp) cover an L2 hit, and whenever the reader enters a new 128-byte line it prefetches the line
+// after the next into L2. Consuming bits is an add and a test; only a word crossing (every ~2.5 codes) moves registers and
+// loads. Words past `nwords` read as zeros: no read leaves the frame's last 16-byte granule. (Earlier versions, for the
+// record: one dependent 32-bit load per refill = ~250 cycles per Rice code; a three-deep queue of 128-bit loads whose
+// rotation cost 5 moves per word; a 64-bit left-aligned accumulator whose branch-free refill cost ~14 instructions per code.)
 struct BitRd {
-	const uint32_t *words;         // 4-byte aligned address at or below the frame's first byte
+	const uint32_t *words;         // 128-byte aligned address at or below the frame's first byte
 	uint32_t nwords;               // words (from `words`) that may be read
-	uint32_t widx;                 // index of the next word to LOAD (nextw holds word widx - 1)
+	uint32_t widx;                 // index of the next word to LOAD (w3 holds word widx - 1, w0 word widx - 4 = pos >> 5)
 	uint32_t pos, end;             // bit position / end of the frame, relative to `words`
-	uint32_t nextw;                // look-ahead word, already byte-swapped
-	unsigned long long acc;
-	int nbits;
+	uint32_t w0, w1, w2, w3;       // byte-swapped words
 	__device__ __forceinline__ uint32_t load(uint32_t i) const
 	{
 		uint32_t v = 0u;
 		if(i < nwords) v = __ldg(words + i);
 		return __byte_perm(v, 0, 0x0123);
 	}
-	__device__ __forceinline__ void prefetch_ahead(uint32_t i) const
+	__device__ __forceinline__ void prefetch_line(uint32_t i) const  // i: first word of a 128-byte line
 	{
-		// i = index of a word in a new 128-byte line (relative to an aligned `words`, lines start at multiples of 32 words)
-		if(i + 64u < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + i + 64u));
+		if(i < nwords) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + i));
 	}
-	__device__ __forceinline__ void refill()
-	{
-		const bool need = nbits <= 32;
-		const unsigned long long add = (unsigned long long)nextw << ((32 - nbits) & 63);
-		acc |= need ? add : 0ull;
-		nbits += need ? 32 : 0;
-		if(need) {
-			nextw = load(widx);
-			if((widx & 31u) == 0u) prefetch_ahead(widx);
-			widx++;
-		}
-	}
-	__device__ __forceinline__ void reseat()  // (re)build the accumulator at bit position `pos`
+	__device__ __forceinline__ void reseat()  // (re)load the window at bit position `pos`
 	{
 		widx = pos >> 5;
-		const uint32_t hi = load(widx), lo = load(widx + 1u);
-		nextw = load(widx + 2u);
-		prefetch_ahead(widx & ~31u);
-		if(((widx & ~31u) + 32u) < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (widx & ~31u) + 32u));
-		widx += 3u;
-		acc = ((unsigned long long)hi << 32) | lo;
-		nbits = 64;
-		const uint32_t r = pos & 31u;
-		acc <<= r;
-		nbits -= (int)r;
-		refill();
+		w0 = load(widx); w1 = load(widx + 1u); w2 = load(widx + 2u); w3 = load(widx + 3u);
+		prefetch_line((widx & ~31u) + 32u);
+		prefetch_line((widx & ~31u) + 64u);
+		widx += 4u;
 	}
 	// p: first byte of the frame, len: frame bytes, bit: bit offset inside the frame to start at
 	__device__ __forceinline__ void init(const uint8_t *p, uint32_t len, uint32_t bit)
@@ -129,23 +108,28 @@ struct BitRd {
 		pos = lead + bit;
 		reseat();
 	}
-	__device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(acc >> 32); }
+	__device__ __forceinline__ uint32_t peek32() const { return __funnelshift_l(w1, w0, pos); }  // shift amount wraps at 32
 	__device__ __forceinline__ void consume(uint32_t n)  // 0..32
 	{
-		acc <<= n;
-		nbits -= (int)n;
-		pos += n;
-		refill();
+		const uint32_t np = pos + n;
+		const bool cross = ((pos ^ np) & 32u) != 0u;  // n <= 32: at most one word boundary
+		pos = np;
+		if(cross) {
+			w0 = w1; w1 = w2; w2 = w3;
+			w3 = load(widx);
+			if((widx & 31u) == 0u) prefetch_line(widx + 64u);
+			widx++;
+		}
 	}
 	__device__ __forceinline__ uint32_t get(uint32_t n)  // 1..32
 	{
-		const uint32_t v = peek32() >> (32 - n);
+		const uint32_t v = peek32() >> (32u - n);
 		consume(n);
 		return v;
 	}
 	__device__ __forceinline__ int32_t get_signed(uint32_t n)  // 1..32
 	{
-		const int32_t v = (int32_t)peek32() >> (32 - n);
+		const int32_t v = (int32_t)peek32() >> (32u - n);
 		consume(n);
 		return v;
 	}
@@ -383,8 +367,8 @@ __global__ void __launch_bounds__(128) k_dec_walk(DecK P, const uint8_t *__restr
 					else {
 						for(; i < pend; i++) {
 							// one Rice code: zeros, a one, k low bits
-							uint32_t v = br.peek32();
-							if(v != 0 && (uint32_t)__clz((int)v) + 1 + k <= 32u) br.consume((uint32_t)__clz((int)v) + 1 + k);
+							const uint32_t n = (uint32_t)__clz((int)br.peek32()) + 1u + k;  // clz(0) = 32
+							if(n <= 32u) br.consume(n);
 							else { (void)br.unary(); br.skip(k); }
 						}
 					}
@@ -401,106 +385,153 @@ __global__ void __launch_bounds__(128) k_dec_walk(DecK P, const uint8_t *__restr
 // One lane per (frame, channel); CHL lanes per frame (channels rounded up to a power of two), 32 / CHL frames per warp.
 // The lanes run in lock step over the sample index i; sample i of a lane lives in history slot i % MAXORD, and the loop
 // is unrolled MAXORD times so that every history access has a compile-time register index.
-template <int MAXORD, bool WIDE>
-__device__ __forceinline__ void dec_lane_loop(BitRd &br, const bool live, const uint32_t bs_lane, const uint32_t bs_max, const uint32_t type,
-                                              const uint32_t order, const uint32_t sbps, const uint32_t wasted, const int shift, const bool lane_wide,
-                                              const int (&q)[MAXORD], const int (&warm)[MAXORD], const int32_t cval, const uint32_t po, const uint32_t plen,
-                                              const uint32_t pesc, int32_t *__restrict__ dst, const uint32_t ch, const uint32_t ca, const uint32_t cidx,
+// The rare events of the sample loop live out of line (by value in, by value out: the reader stays in registers on the hot path):
+// the loop body is unrolled MAXORD times, and with every slow path inlined at every site it outgrew the instruction cache
+// (18 % of the stall samples were instruction fetches).
+struct DecPart {
+	uint32_t k, raw, next_part, part_end, esc;
+};
+struct DecPartOut {
+	BitRd br;
+	DecPart st;
+};
+// a partition starts at sample i (or the lane's block ended): Rice parameter (+ escape width), stream_decoder.c:3299-3357
+__device__ __noinline__ DecPartOut dec_partition_start(BitRd br, DecPart st, uint32_t i, uint32_t bs_lane, uint32_t psamples, uint32_t plen, uint32_t pesc)
+{
+	do {
+		if(i >= bs_lane) { st.esc = 1; st.raw = 0; st.next_part = 0xffffffffu; break; }
+		st.k = br.get(plen);
+		st.esc = st.k >= pesc;
+		if(st.esc) st.raw = br.get(5);
+		st.next_part = st.part_end;
+		st.part_end += psamples;
+	} while(i == st.next_part);
+	DecPartOut o;
+	o.br = br; o.st = st;
+	return o;
+}
+struct DecCodeOut {
+	BitRd br;
+	uint32_t uu;
+};
+// a Rice code whose unary part and k low bits do not fit the 32-bit window
+__device__ __noinline__ DecCodeOut dec_long_code(BitRd br, uint32_t k)
+{
+	const uint32_t msbs = br.unary();
+	DecCodeOut o;
+	o.uu = (msbs << k) | (k ? br.get(k) : 0u);
+	o.br = br;
+	return o;
+}
+
+// Every subframe type runs through ONE loop body: CONSTANT is a first-order predictor with one warm-up sample and all-zero
+// residuals, VERBATIM a zero predictor whose residuals are escape-coded with the sample width; both enter as an "escaped
+// partition" that spans the block (esc0 / raw0), so the body has no per-sample type test. A lane that is past its block (or has
+// no block) is switched into the same zero-width escape mode at the partition-start test, reads nothing and stores nothing.
+template <int MAXORD, bool WIDE, int CH>
+__device__ __forceinline__ void dec_lane_loop(BitRd &br, const uint32_t bs_lane, const uint32_t bs_max, const uint32_t order, const uint32_t wasted,
+                                              const int shift, const bool lane_wide, const int (&q)[MAXORD], const int (&warm)[MAXORD],
+                                              const bool esc0, const uint32_t raw0, const uint32_t po, const uint32_t plen, const uint32_t pesc,
+                                              int32_t *__restrict__ dst, const uint32_t ch_rt, const uint32_t ca, const uint32_t cidx,
                                               const uint32_t out_bps, bool &bad)
 {
+	const uint32_t ch = CH ? (uint32_t)CH : ch_rt;
 	int H[MAXORD];
 #pragma unroll
 	for(int j = 0; j < MAXORD; j++) H[j] = 0;
-	const uint32_t psamples = po ? (bs_lane >> po) : bs_lane;
-	uint32_t next_part = order, k = 0, raw = 0;
-	bool esc = false;
+	const uint32_t psamples = bs_lane >> po;
+	DecPart st;
+	st.k = 0; st.raw = raw0; st.next_part = esc0 ? bs_lane : order; st.part_end = psamples; st.esc = esc0 ? 1u : 0u;
 	const uint32_t lim = 1u << (out_bps - 1);
-	// how this lane's output is formed from its own value and its partner's (stream_decoder.c:3476-3527):
-	// 0 own value, 1 right = left - side, 2 left = side + right, 3 left of mid/side, 4 right of mid/side
-	const int omode = ch != 2 ? 0 : ca == 1 ? (cidx ? 1 : 0) : ca == 2 ? (cidx ? 0 : 2) : ca == 3 ? (cidx ? 4 : 3) : 0;
+	uint32_t range_or = 0;  // OR of (sample + lim): any bit at or above out_bps = a sample out of range (stream_decoder.c:2458-2472)
+	// how this lane's output is formed from its own value v and its partner's o (stream_decoder.c:3476-3527), as
+	// (ca * v + cb * o + (o & mo) + (v & mv)) >> cs: own value; right = left - side; left = side + right; mid/side: the lane that
+	// holds mid: ((mid << 1 | side & 1) + side) >> 1, the lane that holds side: ((mid << 1 | side & 1) - side) >> 1
+	int cA = 1, cB = 0, cs = 0;
+	uint32_t mo = 0, mv = 0;
+	if(ch == 2) {
+		if(ca == 1 && cidx == 1) { cA = -1; cB = 1; }
+		else if(ca == 2 && cidx == 0) { cA = 1; cB = 1; }
+		else if(ca == 3 && cidx == 0) { cA = 2; cB = 1; cs = 1; mo = 1; }
+		else if(ca == 3 && cidx == 1) { cA = -1; cB = 2; cs = 1; mv = 1; }
+	}
 	int32_t *op = dst;
 
-	// one sample; FIRST: the first MAXORD samples of the block, where warm-up samples may still come straight from the header
+	// one sample; FIRST: the first MAXORD samples of the block, where warm-up samples still come straight from the header
 	auto step = [&](auto first_tag, const int u, const uint32_t i) {
 		constexpr bool FIRST = decltype(first_tag)::value;
-		const bool on = live && i < bs_lane;
-		int32_t x = 0;
-		if(on) {
-			if(type == 0) x = cval;                                   // CONSTANT
-			else if(type == 1) x = br.get_signed(sbps);              // VERBATIM
-			else if(FIRST && i < order) x = warm[u];                 // warm-up
-			else {
-				if(i == next_part) {                                  // a partition starts: parameter (+ escape width)
-					k = br.get(plen);
-					esc = k >= pesc;
-					if(esc) raw = br.get(5);
-					next_part = po ? (i / psamples + 1) * psamples : bs_lane;
-				}
-				int32_t r;
-				if(!esc) {
-					// deduplication/bitreader_read_rice_signed_block.c: unary MSBs, k LSBs, zig-zag
-					const uint32_t v = br.peek32();
-					const uint32_t z = (uint32_t)__clz((int)v);
-					uint32_t uu;
-					if(v != 0 && z + 1 + k <= 32u) {
-						const uint32_t low = k ? ((v << (z + 1)) >> (32u - k)) : 0u;
-						uu = (z << k) | low;
-						br.consume(z + 1 + k);
-					}
-					else {
-						const uint32_t msbs = br.unary();
-						uu = (msbs << k) | (k ? br.get(k) : 0u);
-					}
-					r = (int32_t)(uu >> 1) ^ -(int32_t)(uu & 1u);
-				}
-				else r = raw ? br.get_signed(raw) : 0;
-				// prediction from the last `order` samples: x[i-1-j] sits in slot (u - 1 - j) mod MAXORD
-				int32_t pred;
-				if(WIDE && lane_wide) {
-					long long s0 = 0, s1 = 0;
-#pragma unroll
-					for(int j = 0; j < MAXORD; j += 2) {
-						s0 += (long long)q[j] * (long long)H[(u - 1 - j + 2 * MAXORD) % MAXORD];
-						if(j + 1 < MAXORD) s1 += (long long)q[j + 1] * (long long)H[(u - 2 - j + 2 * MAXORD) % MAXORD];
-					}
-					pred = (int32_t)((s0 + s1) >> shift);
+		int32_t x;
+		if(FIRST && i < order) x = warm[u];
+		else {
+			if(i == st.next_part) {
+				const DecPartOut o = dec_partition_start(br, st, i, bs_lane, psamples, plen, pesc);
+				br = o.br; st = o.st;
+			}
+			int32_t r;
+			if(!st.esc) {
+				// deduplication/bitreader_read_rice_signed_block.c: unary MSBs, k LSBs, zig-zag
+				const uint32_t v = br.peek32();
+				const uint32_t z = (uint32_t)__clz((int)v);  // 32 for v == 0
+				uint32_t uu;
+				if(z + 1u + st.k <= 32u) {
+					const uint32_t low = ((v << z) & 0x7fffffffu) >> (31u - st.k);  // the k bits after the terminating 1
+					uu = (z << st.k) | low;
+					br.consume(z + 1u + st.k);
 				}
 				else {
-					int s0 = 0, s1 = 0;
-#pragma unroll
-					for(int j = 0; j < MAXORD; j += 2) {
-						s0 += q[j] * H[(u - 1 - j + 2 * MAXORD) % MAXORD];
-						if(j + 1 < MAXORD) s1 += q[j + 1] * H[(u - 2 - j + 2 * MAXORD) % MAXORD];
-					}
-					pred = (s0 + s1) >> shift;
+					const DecCodeOut o = dec_long_code(br, st.k);
+					br = o.br; uu = o.uu;
 				}
-				x = r + pred;
+				r = (int32_t)(uu >> 1) ^ -(int32_t)(uu & 1u);
 			}
-			H[u] = x;
+			else r = st.raw ? br.get_signed(st.raw) : 0;
+			// prediction from the last `order` samples: x[i-1-j] sits in slot (u - 1 - j) mod MAXORD
+			int32_t pred;
+			if(WIDE && lane_wide) {
+				long long s0 = 0, s1 = 0;
+#pragma unroll
+				for(int j = 0; j < MAXORD; j += 2) {
+					s0 += (long long)q[j] * (long long)H[(u - 1 - j + 2 * MAXORD) % MAXORD];
+					if(j + 1 < MAXORD) s1 += (long long)q[j + 1] * (long long)H[(u - 2 - j + 2 * MAXORD) % MAXORD];
+				}
+				pred = (int32_t)((s0 + s1) >> shift);
+			}
+			else {
+				int s0 = 0, s1 = 0;
+#pragma unroll
+				for(int j = 0; j < MAXORD; j += 2) {
+					s0 += q[j] * H[(u - 1 - j + 2 * MAXORD) % MAXORD];
+					if(j + 1 < MAXORD) s1 += q[j + 1] * H[(u - 2 - j + 2 * MAXORD) % MAXORD];
+				}
+				pred = (s0 + s1) >> shift;
+			}
+			x = r + pred;
 		}
+		H[u] = x;
 		// ---- undo the channel decorrelation and store interleaved
 		const int32_t val = (int32_t)((uint32_t)x << wasted);
 		int32_t out = val;
 		if(ch == 2) {
 			const int32_t other = __shfl_xor_sync(0xffffffffu, val, 1);
-			const int32_t m2a = (int32_t)(((uint32_t)val << 1) | ((uint32_t)other & 1u)), m2b = (int32_t)(((uint32_t)other << 1) | ((uint32_t)val & 1u));
-			out = omode == 0 ? val : omode == 1 ? other - val : omode == 2 ? val + other : omode == 3 ? (m2a + other) >> 1 : (m2b - val) >> 1;
+			out = (cA * val + cB * other + (int32_t)((uint32_t)other & mo) + (int32_t)((uint32_t)val & mv)) >> cs;
 		}
-		if(on) {
-			if((uint32_t)out + lim >= 2u * lim) bad = true;  // stream_decoder.c:2458-2472 OUT_OF_BOUNDS
-			*op = out;
-		}
-		op += ch;
+		const bool on = i < bs_lane;
+		range_or |= on ? (uint32_t)out + lim : 0u;
+		if(on) op[(CH ? (uint32_t)u : 0u) * ch] = out;
+		if(!CH) op += ch;
 	};
 	if(bs_max > 0) {
 #pragma unroll
 		for(int u = 0; u < MAXORD; u++) step(std::true_type{}, u, (uint32_t)u);
+		if(CH) op += MAXORD * CH;
 	}
 #pragma unroll 1
 	for(uint32_t i0 = MAXORD; i0 < bs_max; i0 += MAXORD) {
 #pragma unroll
 		for(int u = 0; u < MAXORD; u++) step(std::false_type{}, u, i0 + (uint32_t)u);
+		if(CH) op += MAXORD * CH;
 	}
+	if(range_or >> out_bps) bad = true;
 }
 
 template <int MAXQ>
@@ -613,16 +644,23 @@ __global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__res
 	int32_t *dst = pcm + (size_t)first * ch + cidx;
 	const bool any_wide = __any_sync(0xffffffffu, lane_wide && live);
 	const uint32_t bs_eff = live ? bs_lane : 0u;
-	const uint32_t ltype = live ? h.type : 0u;
 
+	// CONSTANT: one warm-up sample, first-order predictor, no residual bits; VERBATIM: escape-coded "residuals" of the sample width
+	bool esc0 = !live;
+	uint32_t raw0 = 0, order_eff = order;
+	if(live && h.type == 0) { esc0 = true; order_eff = 1; wbuf[0] = cval; qbuf[0] = 1; }
+	if(live && h.type == 1) { esc0 = true; raw0 = h.bps; }
+	if(!live) order_eff = 0;
+
+#define FB200_DEC_RUN2(MO, WD, CHT)                                                                                                          \
+	dec_lane_loop<MO, WD, CHT>(br, bs_eff, bs_max, order_eff, h.wasted, shift, WD && lane_wide, q, w, esc0, raw0, po, plen, pesc, dst, (uint32_t)ch,  \
+	                           ca, cidx, bps, bad)
 #define FB200_DEC_RUN(MO)                                                                                                                    \
 	do {                                                                                                                                       \
 		int q[MO], w[MO];                                                                                                                      \
-		_Pragma("unroll") for(int j = 0; j < MO; j++) { q[j] = qbuf[j < MAXQ ? j : 0]; w[j] = wbuf[j < MAXQ ? j : 0]; }                                                     \
-		if(any_wide) dec_lane_loop<MO, true>(br, live, bs_eff, bs_max, ltype, order, h.bps, h.wasted, shift, lane_wide, q, w, cval, po, plen,   \
-		                                     pesc, dst, (uint32_t)ch, ca, cidx, bps, bad);                                                     \
-		else dec_lane_loop<MO, false>(br, live, bs_eff, bs_max, ltype, order, h.bps, h.wasted, shift, false, q, w, cval, po, plen, pesc, dst,    \
-		                              (uint32_t)ch, ca, cidx, bps, bad);                                                                       \
+		_Pragma("unroll") for(int j = 0; j < MO; j++) { q[j] = qbuf[j < MAXQ ? j : 0]; w[j] = wbuf[j < MAXQ ? j : 0]; }                       \
+		if(any_wide) { if(ch == 2) FB200_DEC_RUN2(MO, true, 2); else FB200_DEC_RUN2(MO, true, 0); }                                            \
+		else { if(ch == 2) FB200_DEC_RUN2(MO, false, 2); else FB200_DEC_RUN2(MO, false, 0); }                                                  \
 	} while(0)
 	if(MAXQ == 12) {
 		if(omax <= 8) FB200_DEC_RUN(8);
@@ -630,6 +668,7 @@ __global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__res
 	}
 	else FB200_DEC_RUN(MAXQ);
 #undef FB200_DEC_RUN
+#undef FB200_DEC_RUN2
 
 	// ---- frame end: padding to a byte boundary + CRC-16 must end at (or, in index mode, before) the given end
 	uint32_t status = M.status;

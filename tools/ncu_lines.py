@@ -2,7 +2,9 @@
 
     ncu -i rep.ncu-rep --page source --csv --kernel-name regex:k_search3 > sass.csv
     cuobjdump -xelf all libflac_b200.so ; nvdisasm -g -c encoder.sm_100a.cubin > dis.txt
-    python tools/ncu_lines.py sass.csv dis.txt <mangled-function-name> [top]
+    python tools/ncu_lines.py sass.csv[.gz] dis.txt <mangled-function-name> [top] [kernel-name-substring]
+
+With several kernels in one export, the last argument picks the launch whose demangled name contains it (default: first).
 
 Joins by instruction order (the ncu export lists the function's SASS in program order).
 Inlined code is attributed to the innermost line nvdisasm reports."""
@@ -15,8 +17,15 @@ from collections import defaultdict
 def main():
     sass_csv, dis, func = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    rows = list(csv.reader(open(sass_csv)))
-    hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
+    pick = sys.argv[5] if len(sys.argv) > 5 else None
+    import gzip
+    import io
+    fh = io.TextIOWrapper(gzip.open(sass_csv)) if sass_csv.endswith(".gz") else open(sass_csv)
+    rows = list(csv.reader(fh))
+    his = [i for i, r in enumerate(rows) if "Instructions Executed" in r]
+    hi = his[0]
+    if pick:
+        hi = next(i for i in his if i > 0 and pick in ",".join(rows[i - 1]))
     h = rows[hi]
     ie, ss, so = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")
     inst = []
