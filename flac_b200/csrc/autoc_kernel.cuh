@@ -170,7 +170,7 @@ __host__ __device__ constexpr size_t autoc4_smem_bytes(int nsig, int ch, int mod
 template <int LAGS, int U, int K, int STAGES, int MODE>
 __global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict__ pcm, const SigMeta *__restrict__ meta,
                                               const float *__restrict__ secwin, int secwin_stride, const DevSection *__restrict__ secs,
-                                              double *__restrict__ autoc, int nitems)
+                                              double *__restrict__ autoc, int nitems, uint32_t *__restrict__ sigor, int or_sec)
 {
 	static_assert(U % LAGS == 0 && U % 4 == 0, "a body must be a whole number of history rotations and of 128-bit loads");
 	constexpr int T = U * K;
@@ -184,6 +184,11 @@ __global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict
 	// section slowest: the longest chains (full-length sections) start first (see k_autoc3)
 	const int groups = (nitems + 31) >> 5;
 	const int sec = blockIdx.x / groups;
+	// sigor: the chains of section or_sec (a full-length one) also OR their samples together -- all get_wasted_bits_ needs
+	// (stream_encoder.c:5077-5099); k_lpc turns the word into the signal's wasted bits / subframe bps, and no kernel has to
+	// read the block just for that
+	const bool do_or = sigor != nullptr && sec == or_sec;
+	uint32_t orv = 0;
 	const int item0 = (blockIdx.x - sec * groups) << 5;
 	const int item = min(item0 + lane, nitems - 1);
 	// meta == nullptr: the wasted-bits shift is left to k_lpc (the windowed products and their sums scale EXACTLY by powers of
@@ -243,6 +248,14 @@ __global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict
 		__syncwarp();                 // every lane is done with tile t-1's buffer ...
 		issue(t + STAGES - 1);        // ... which is the one refilled now
 		mbar_wait(&bars[t % STAGES], (unsigned)(t / STAGES) & 1u);
+		if(do_or && bs - (a0 + t * T) < T) {
+			// the block's last tile is short: what lies behind it in the buffer is stale, weighted 0 in the sums but not in the OR
+			const int n = bs - (a0 + t * T);
+			int *st = smem + (t % STAGES) * STAGE_WORDS;
+			for(int r = 0; r < nrows; r++)
+				for(int i = n * ch + lane; i < T * ch; i += 32) st[r * RS + i] = 0;
+			__syncwarp();
+		}
 		const int *row = smem + (t % STAGES) * STAGE_WORDS + myrow * RS;
 		const float *win = reinterpret_cast<const float *>(smem + (t % STAGES) * STAGE_WORDS + autoc4_rows_max(nsig) * RS);
 #pragma unroll 1
@@ -266,6 +279,7 @@ __global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict
 				}
 				const float4 wq = *reinterpret_cast<const float4 *>(win + kb * U + q * 4);
 				const float ws[4] = {wq.x, wq.y, wq.z, wq.w};
+				orv |= (uint32_t)(xs4[0] | xs4[1]) | (uint32_t)(xs4[2] | xs4[3]);
 #pragma unroll
 				for(int e = 0; e < 4; e++) {
 					const int u = q * 4 + e;
@@ -282,6 +296,7 @@ __global__ void __launch_bounds__(32) k_autoc4(EncK P, const int32_t *__restrict
 		double *out = autoc + ((size_t)sec * nitems + item) * P.lag_stride;
 #pragma unroll
 		for(int l = 0; l < LAGS; l++) out[l] = acc[l];
+		if(do_or) sigor[item] = orv;
 	}
 }
 

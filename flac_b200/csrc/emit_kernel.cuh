@@ -24,6 +24,8 @@
 //     directly to out + offset.
 #pragma once
 
+#include <type_traits>
+
 #include "device_common.cuh"
 #include "search_kernel.cuh"  // row layout constants (kSearch4ZeroRow)
 
@@ -80,27 +82,24 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 	asm volatile("st.volatile.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 
+// Bit packer of one run (the paths whose Rice parameter changes inside a run, and verbatim subframes). Store discipline of
+// the pack pass: a word is plain-stored by the one run whose bits reach the word's last bit; a run's trailing partial word is
+// NOT written by it but handed back (last_word / last_bits) and OR-ed in after the CTA barrier that ends the pass, together
+// with the header fields -- so the pass itself has no atomics and no read-modify-write.
 struct RunPacker {
 	uint32_t *words;
 	uint32_t cur, pos;
 	int widx;
-	bool shared_first;
 	__device__ __forceinline__ void init(uint32_t *w, uint32_t bitpos)
 	{
-		words = w; pos = bitpos; widx = (int)(bitpos >> 5); cur = 0; shared_first = true;
-	}
-	__device__ __forceinline__ void store()
-	{
-		if(shared_first) { if(cur) atomicOr(&words[widx], cur); }
-		else words[widx] = cur;  // interior word: exclusively this run's, buffer pre-zeroed
-		shared_first = false;
+		words = w; pos = bitpos; widx = (int)(bitpos >> 5); cur = 0;
 	}
 	// n zero bits
 	__device__ __forceinline__ void skip(uint32_t n)
 	{
 		pos += n;
 		const int nw = (int)(pos >> 5);
-		if(nw != widx) { if(cur || !shared_first) store(); shared_first = false; widx = nw; cur = 0; }
+		if(nw != widx) { words[widx] = cur; widx = nw; cur = 0; }  // words skipped over entirely stay zero (pre-zeroed buffer)
 	}
 	// 1..32 bits, value < 2^nbits
 	__device__ __forceinline__ void put(uint32_t value, uint32_t nbits)
@@ -110,14 +109,10 @@ struct RunPacker {
 		cur |= (uint32_t)(v >> 32);
 		pos += nbits;
 		if(off + nbits >= 32u) {
-			store();
+			words[widx] = cur;
 			widx++;
 			cur = (uint32_t)v;
 		}
-	}
-	__device__ __forceinline__ void finish()
-	{
-		if(cur) atomicOr(&words[widx], cur);  // last (partial) word may be shared with the next run
 	}
 };
 
@@ -505,8 +500,95 @@ __global__ void __launch_bounds__(256, WIDEK ? 3 : 4) k_emit3(EncK P, Emit3Args 
 		if(!fits) atomicExch(A.err, 2);
 	}
 
-	// ---- pass 2: pack
+	// ---- pass 2: pack. Before the barrier: plain stores only (a word is stored by the run that reaches its last bit); after
+	// it: every run's trailing partial word, the frame header and the subframe header fields are OR-ed in.
+	int last_word = 0;
+	uint32_t last_bits = 0;
 	if(fits) {
+		// residual codes of this run (stream_encoder_framing.c:538-594, bitwriter.c:575-706)
+		if(predicted) {
+			if(one_partition) {
+				// ONE partition per run: zeros + stop bit + k low bits go out as one field of n = q + k + 1 bits; the pending word
+				// `cur` (fill bits used) is stored when it completes. Every run -- the one with the warm-up samples included --
+				// runs this same loop (skipn leading samples are not residuals), so the warps of a frame finish together.
+				const uint32_t k = k_run, k1 = k + 1;
+				const uint32_t stop = 1u << k, lowmask = stop - 1u;
+				const uint32_t pos0 = bit0 + start + pre;
+				int widx = (int)(pos0 >> 5);
+				uint32_t fill = pos0 & 31u, cur = 0;
+				auto put = [&](uint32_t val, uint32_t n) {  // 0 <= n <= 32, val < 2^n; branch-free: the store is predicated
+					const unsigned long long t = (unsigned long long)val << (64u - fill - n);
+					cur |= (uint32_t)(t >> 32);
+					const uint32_t f2 = fill + n;
+					const bool full = f2 >= 32u;
+					if(full) words[widx] = cur;
+					cur = full ? (uint32_t)t : cur;
+					widx += (int)(f2 >> 5);
+					fill = f2 & 31u;
+				};
+				const int pidx = base / psize;
+				const int skipn = order > base ? order - base : 0;                       // leading warm-up samples of this run
+				const int prel = (pidx == 0 ? order : pidx * psize) - base;               // the partition's first residual, relative to the run
+				// partitions are whole runs here: the parameter, if this run carries one, sits in front of its first coded sample
+				if(prel == skipn && skipn < R_T) put(k, plen);
+				auto pack_run = [&](auto skip_tag) {
+					constexpr bool SKIP = decltype(skip_tag)::value;  // only the run that holds the warm-up samples tests for them
+#pragma unroll 1
+					for(int v4 = 0; v4 < R_T / 4; v4++) {
+						const uint4 uv = *reinterpret_cast<const uint4 *>(rowp + 4 * v4);
+#pragma unroll
+						for(int e = 0; e < 4; e++) {
+							const int m = 4 * v4 + e;
+							if(SKIP && m < skipn) continue;
+							const uint32_t u = e == 0 ? uv.x : e == 1 ? uv.y : e == 2 ? uv.z : uv.w;
+							const uint32_t qz = u >> k;
+							const uint32_t val = stop | (u & lowmask);
+							if(qz + k1 <= 32u) put(val, qz + k1);
+							else {
+								// a long unary run (rare): zeros word by word, then the stop bit + low bits
+								uint32_t z = qz;
+								while(z) { const uint32_t c = z < 32u - fill ? z : 32u - fill; put(0u, c); z -= c; }
+								put(val, k1);
+							}
+						}
+					}
+				};
+				if(skipn) pack_run(std::true_type{});
+				else pack_run(std::false_type{});
+				last_word = widx; last_bits = cur;
+			}
+			else {
+				// partitions shorter than a run (partition orders above log2(bs / R_T)): the parameter changes inside the run
+				RunPacker pk;
+				pk.init(words, bit0 + start + pre);
+				int p = base / psize;
+				int next = (p + 1) * psize;
+				uint32_t k = __ldg(&pl->params[p]);
+#pragma unroll 1
+				for(int m = 0; m < R_T; m++) {
+					const int i = base + m;
+					if(i >= order) {
+						if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
+						if(i == p * psize || i == order) pk.put(k, plen);
+						const uint32_t u = (uint32_t)rowp[m];
+						pk.skip(u >> k);
+						pk.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
+					}
+				}
+				last_word = pk.widx; last_bits = pk.cur;
+			}
+		}
+		else if(type == SF_VERBATIM) {
+			RunPacker pk;
+			pk.init(words, bit0 + start + pre);
+#pragma unroll 1
+			for(int m = 0; m < R_T; m++) pk.put(mask_bits(rowp[m], (uint32_t)sbps), (uint32_t)sbps);
+			last_word = pk.widx; last_bits = pk.cur;
+		}
+	}
+	__syncthreads();
+	if(fits) {
+		if(last_bits) atomicOr(&words[last_word], last_bits);
 		if(warp == (NT >> 5) - 1 && lane < 5) {
 			// place the pre-built frame header at byte s0 (S.hdr was written before the barriers above)
 			const uint32_t sh = 8 * s0;
@@ -577,89 +659,7 @@ __global__ void __launch_bounds__(256, WIDEK ? 3 : 4) k_emit3(EncK P, Emit3Args 
 				}
 			}
 		}
-		// residual codes of this run (stream_encoder_framing.c:538-594, bitwriter.c:575-706)
-		if(predicted) {
-			if(one_partition) {
-				// ONE partition per run: zeros + stop bit + k low bits go out as one field of n = q + k + 1 bits; the pending word
-				// `cur` (fill bits used) spills into `words` when it completes. Only the run's first word can be shared with the
-				// previous run: it is kept in `fw` and OR-ed in at the end, so the loop has plain stores only. Every run -- the one
-				// with the warm-up samples included -- runs this same loop (skipn leading samples are not residuals; the partition
-				// parameter goes in front of sample prel), so the warps of a frame finish together.
-				const uint32_t k = k_run, k1 = k + 1;
-				const uint32_t stop = 1u << k, lowmask = stop - 1u;
-				const uint32_t pos0 = bit0 + start + pre;
-				const int w0 = (int)(pos0 >> 5);
-				int widx = w0, wshared = w0;
-				uint32_t fill = pos0 & 31u, cur = 0, fw = 0;
-				auto put = [&](uint32_t val, uint32_t n) {  // 1 <= n <= 32, val < 2^n
-					const unsigned long long t = (unsigned long long)val << (64u - fill - n);
-					cur |= (uint32_t)(t >> 32);
-					fill += n;
-					if(fill >= 32u) {
-						if(widx != wshared) words[widx] = cur;
-						else { fw = cur; wshared = -1; }
-						widx++;
-						cur = (uint32_t)t;
-						fill -= 32u;
-					}
-				};
-				const int pidx = base / psize;
-				const int skipn = order > base ? order - base : 0;                       // leading warm-up samples of this run
-				const int prel = (pidx == 0 ? order : pidx * psize) - base;               // the partition's first residual, relative to the run
-#pragma unroll 1
-				for(int v4 = 0; v4 < R_T / 4; v4++) {
-					const uint4 uv = *reinterpret_cast<const uint4 *>(rowp + 4 * v4);
-#pragma unroll
-					for(int e = 0; e < 4; e++) {
-						const int m = 4 * v4 + e;
-						if(m < skipn) continue;
-						if(m == prel) put(k, plen);
-						const uint32_t u = e == 0 ? uv.x : e == 1 ? uv.y : e == 2 ? uv.z : uv.w;
-						const uint32_t qz = u >> k;
-						const uint32_t val = stop | (u & lowmask);
-						if(qz + k1 <= 32u) put(val, qz + k1);
-						else {
-							// a long unary run (rare): zeros word by word, then the stop bit + low bits
-							uint32_t z = qz;
-							while(z) { const uint32_t c = z < 32u - fill ? z : 32u - fill; put(0u, c); z -= c; }
-							put(val, k1);
-						}
-					}
-				}
-				// the run's first word (shared with the previous run) and its last, partial word (shared with the next)
-				if(wshared < 0) { if(fw) atomicOr(&words[w0], fw); if(cur) atomicOr(&words[widx], cur); }
-				else if(cur) atomicOr(&words[widx], cur);
-			}
-			else {
-				// partitions shorter than a run (partition orders above log2(bs / R_T)): the parameter changes inside the run
-				RunPacker pk;
-				pk.init(words, bit0 + start + pre);
-				int p = base / psize;
-				int next = (p + 1) * psize;
-				uint32_t k = __ldg(&pl->params[p]);
-#pragma unroll 1
-				for(int m = 0; m < R_T; m++) {
-					const int i = base + m;
-					if(i >= order) {
-						if(i == next) { p++; next += psize; k = __ldg(&pl->params[p]); }
-						if(i == p * psize || i == order) pk.put(k, plen);
-						const uint32_t u = (uint32_t)rowp[m];
-						pk.skip(u >> k);
-						pk.put((1u << k) | (u & ((1u << k) - 1u)), k + 1);
-					}
-				}
-				pk.finish();
-			}
-		}
-		else if(type == SF_VERBATIM) {
-			RunPacker pk;
-			pk.init(words, bit0 + start + pre);
-#pragma unroll 1
-			for(int m = 0; m < R_T; m++) pk.put(mask_bits(rowp[m], (uint32_t)sbps), (uint32_t)sbps);
-			pk.finish();
-		}
 	}
-	__syncthreads();
 
 	// ---- CRC-16 over the frame: equal word chunks aligned to the (word aligned) end, slicing-by-4, GF(2) combine.
 	// The signals are dead: the slicing tables go where they were.

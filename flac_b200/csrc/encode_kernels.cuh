@@ -355,7 +355,8 @@ __device__ __forceinline__ int quantize_coefficients(const float (&lp_coeff)[MO]
 // concurrently with k_meta): autoc(x >> w) = autoc(x) * 2^-2w exactly, applied here.
 template <int MO>
 __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ autoc, const DevCand *__restrict__ cands,
-                                            const SigMeta *__restrict__ meta, CandDesc *__restrict__ out, int nitems, int autoc_unshifted)
+                                            SigMeta *__restrict__ meta, const uint32_t *__restrict__ sigor, CandDesc *__restrict__ out, int nitems,
+                                            int autoc_unshifted)
 {
 	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
 	if(gid >= nitems * P.nwin) return;
@@ -363,7 +364,20 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 	const int per_win = P.nslots / P.nwin;
 	CandDesc *slots = out + ((size_t)item * P.nslots + (size_t)win * per_win);
 	for(int s = 0; s < per_win; s++) slots[s].valid = 0;
-	const int sbps = meta[item].bps;
+	SigMeta M;
+	if(sigor) {
+		// the OR of the signal's samples came with the autocorrelation (k_autoc4): wasted bits and subframe bps as k_meta
+		// derives them (get_wasted_bits_, stream_encoder.c:5077-5099; side channel one bit wider, :3865); every signal is active
+		const uint32_t o = sigor[item];
+		int w = o ? (__ffs((int)o) - 1) : 0;
+		if(w > P.bps) w = P.bps;
+		const int sidx = item % P.nsig;
+		M.wasted = w;
+		M.bps = P.bps - w + ((P.channels == 2 && P.nsig == 4 && sidx == 3) ? 1 : 0);
+		if(win == 0) meta[item] = M;  // k_search5 reads it from here
+	}
+	else M = meta[item];
+	const int sbps = M.bps;
 	if(sbps == 0) return;
 
 	const int max_order = P.max_order;
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 	{
 		const double *a = autoc + ((size_t)C.sec * nitems + item) * P.lag_stride;
 		// 2^-2w (1.0 when nothing is to undo): an exact scaling of every sum
-		const double sc = autoc_unshifted ? __hiloint2double((1023 - 2 * meta[item].wasted) << 20, 0) : 1.0;
+		const double sc = autoc_unshifted ? __hiloint2double((1023 - 2 * M.wasted) << 20, 0) : 1.0;
 		if(C.kind == 0) {
 #pragma unroll
 			for(int l = 0; l <= MO; l++) ac[l] = l <= max_order ? a[l] * sc : 0.0;
@@ -445,6 +459,20 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 		for(int i = 0; i < FB200_MAX_LPC_ORDER; i++) D.qlp[i] = (i < MO && i < order) ? q[i < MO ? i : 0] : 0;
 		D.valid = 1;
 	}
+}
+
+// ================================================================ k_minbr_flags
+// limit_min_bitrate (stream_encoder.c:3874-3879): when every independent channel before the last chose a CONSTANT subframe,
+// the last channel -- and the mid/side pair evaluated after it -- is searched with constant subframes disabled. The first
+// search pass ran every signal with the stream's own settings; this marks the blocks whose last channel / mid / side are
+// searched again (P.redo) with constants off.
+__global__ void k_minbr_flags(EncK P, const SubframePlan *__restrict__ plans, const int *__restrict__ blkflags, int nb, int *__restrict__ flags)
+{
+	const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+	if(blk >= nb) return;
+	bool all_const = blkflags ? (blkflags[blk] & 1) != 0 : true;  // only inside the independent-channel loop
+	for(int c = 0; c + 1 < P.channels; c++) all_const = all_const && plans[(size_t)blk * P.nsig + c].type == SF_CONSTANT;
+	flags[blk] = all_const ? 1 : 0;
 }
 
 // ================================================================ k_search
@@ -598,6 +626,10 @@ __global__ void __launch_bounds__(128) k_search(EncK P, const int32_t *__restric
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ SearchShared S;
 	const int item = blockIdx.x, tid = threadIdx.x, bs = P.bs, nthr = blockDim.x;
+	if(P.redo) {
+		const int blk = item / P.nsig;
+		if(!P.redo[blk] || item - blk * P.nsig < P.channels - 1) return;
+	}
 	int32_t *x = reinterpret_cast<int32_t *>(smem_raw);
 	uint32_t *absr = reinterpret_cast<uint32_t *>(x + P.bs_stride);
 

@@ -43,6 +43,7 @@ struct Geometry {
 	size_t search5_smem = 0;
 	int maxord_t = 8;
 	int emit3_rt = 0;           // 0, or R_T of the resident emit kernel (k_emit3)
+	int or_sec = -1;            // a full-length analysis section (k_autoc4 collects the wasted-bits OR there), or -1
 	size_t emit3_smem = 0;
 };
 
@@ -59,6 +60,7 @@ struct fb200_encoder {
 	int nsig = 0;
 	int32_t *d_sig = nullptr;
 	SigMeta *d_meta = nullptr;
+	uint32_t *d_sigor = nullptr;  // per (block, signal): OR of the samples, written by k_autoc4 (fused wasted-bits detection)
 	int *d_blkflags = nullptr;
 	double *d_autoc = nullptr;
 	CandDesc *d_cdesc = nullptr;
@@ -69,6 +71,7 @@ struct fb200_encoder {
 	unsigned long long *d_running = nullptr;  // [2]: k_emit3 reads [run_cur] and writes [run_cur ^ 1]; k_scan updates [run_cur] in place
 	int run_cur = 0;
 	int *d_err = nullptr;
+	int *d_redo = nullptr;  // [max_blocks] limit_min_bitrate: blocks whose last channel is searched again with constants off
 	// k_emit3: slicing tables, look-back status words, frame tickets
 	uint16_t *d_crc_tab = nullptr;
 	unsigned long long *d_lookback = nullptr;
@@ -79,7 +82,7 @@ struct fb200_encoder {
 	size_t max_nsec = 0, max_nslots = 0, lag_stride = 0;
 	// stage-A outputs are double-buffered so that stage A (prep/autoc/lpc) of sub-batch i+1 can run on
 	// s_a concurrently with stage B (search/emit/scan/gather) of sub-batch i on the caller's stream
-	struct WS { int32_t *d_sig; SigMeta *d_meta; int *d_blkflags; double *d_autoc; CandDesc *d_cdesc; } ws[2] = {};
+	struct WS { int32_t *d_sig; SigMeta *d_meta; int *d_blkflags; double *d_autoc; CandDesc *d_cdesc; uint32_t *d_sigor; } ws[2] = {};
 	cudaStream_t s_a = nullptr, s_meta = nullptr;
 	cudaEvent_t ev_meta_fork = nullptr, ev_meta_done = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
@@ -101,7 +104,7 @@ struct fb200_encoder {
 	int host_chunks = 12;   // chunks per fb200_encode_host call (FB200_HOST_CHUNKS): copy/compute overlap granularity; measured best 8-12 (tools/sweep_host_chunks.py)
 	int pipe_chunks = 1;    // sub-batches per fb200_encode_device call (FB200_PIPE_CHUNKS); see fb200_encode_device
 	int f64b = 0;         // FB200_SEARCH_F64B=1: the second warp of a signal runs on the FP64 pipe (measured SLOWER: -8 2.59 vs 2.02 ms; kept for A/B)
-	int debug_path = 0;   // FB200_DEBUG_PATH bit mask (bisecting aid): 1 = k_prep + k_autoc3 instead of k_meta + k_autoc4, 2 = general search, 4 = general emit
+	int debug_path = 0;   // FB200_DEBUG_PATH bit mask (bisecting aid): 1 = k_prep + k_autoc3 instead of k_autoc4, 2 = general search, 4 = general emit, 8 = k_meta instead of the OR fused into k_autoc4
 	bool use_v1 = false;  // FB200_FORCE_GENERAL_KERNELS=1: run the general kernels for every blocksize (tests)
 	// optional per-kernel CUDA-event timing (bench.py's roofline numbers)
 	bool prof_on = false;
@@ -176,7 +179,10 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		k.min_po = (int)c.min_residual_partition_order < k.max_po ? (int)c.min_residual_partition_order : k.max_po;
 	}
 	k.rice_limit = c.bits_per_sample > 16 ? (int)kRice2Escape : (int)kRiceEscape;
-	k.dis_const = c.disable_constant_subframes; k.dis_fixed = c.disable_fixed_subframes; k.dis_verb = c.disable_verbatim_subframes;
+	k.limit_min_bitrate = c.limit_min_bitrate ? 1 : 0;
+	k.redo = nullptr;
+	k.dis_const = c.disable_constant_subframes || (c.limit_min_bitrate && c.channels == 1);  // mono: the only channel is the last one
+	k.dis_fixed = c.disable_fixed_subframes; k.dis_verb = c.disable_verbatim_subframes;
 	k.slot_stride = round_up((int)max_frame_bytes_for(c, (int)c.blocksize), 16);
 	k.slot_words = k.slot_stride / 4;
 	{
@@ -215,6 +221,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 		}
 	}
 	k.nsec = (int)secs.size();
+	g.or_sec = secs.empty() ? -1 : 0;  // every apodization opens with its full-length section
 	k.nwin = (int)cands.size();
 	k.nslots = k.nwin * (k.exhaustive ? (k.max_order > 0 ? k.max_order : 1) : 1);
 	if((size_t)k.nsec > e->max_nsec || (size_t)k.nslots > e->max_nslots) {
@@ -278,7 +285,7 @@ static int bs_plus_slack(int bs) { return bs + kSecwinSlack; }
 
 static void use_ws(fb200_encoder *e, int b)
 {
-	e->d_sig = e->ws[b].d_sig; e->d_meta = e->ws[b].d_meta; e->d_blkflags = e->ws[b].d_blkflags;
+	e->d_sig = e->ws[b].d_sig; e->d_meta = e->ws[b].d_meta; e->d_blkflags = e->ws[b].d_blkflags; e->d_sigor = e->ws[b].d_sigor;
 	e->d_autoc = e->ws[b].d_autoc; e->d_cdesc = e->ws[b].d_cdesc;
 }
 
@@ -288,11 +295,15 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	EncK k = g.k;
 	const int nitems = nb * k.nsig;
 	prof_mark(e, -1, st);
-	const bool raw = g.raw_pipeline && !e->use_v1 && e->debug_path == 0 && ((uintptr_t)d_pcm & 15) == 0;
-	// k_meta (HBM-bound) and k_autoc4 (FP64-bound) both only read the caller's PCM: they run concurrently on two streams when the
-	// autocorrelation does not need the meta data (it does under loose mid-side, to skip the inactive pair); k_lpc joins them
-	const bool overlap = raw && k.nwin > 0 && !k.loose_ms && !e->prof_on;
-	if(overlap) {
+	const bool raw = g.raw_pipeline && !e->use_v1 && (e->debug_path & 7) == 0 && ((uintptr_t)d_pcm & 15) == 0;
+	// Wasted-bits detection needs nothing but the OR of a signal's samples. With a full-length analysis section k_autoc4 collects
+	// it on the way (its chains read every sample anyway) and k_lpc derives wasted bits / subframe bps: no kernel reads the block
+	// just for that. Otherwise k_meta does it -- concurrently with k_autoc4 on a second stream when the autocorrelation does not
+	// need the meta data (it does under loose mid-side, to skip the inactive pair); k_lpc joins them.
+	const bool fused = raw && k.nwin > 0 && !k.loose_ms && g.or_sec >= 0 && g.fast_search3 && g.emit3_rt && !(e->debug_path & 8);
+	const bool overlap = !fused && raw && k.nwin > 0 && !k.loose_ms && !e->prof_on;
+	if(fused) {}
+	else if(overlap) {
 		FB_CUDA(cudaEventRecord(e->ev_meta_fork, st));
 		FB_CUDA(cudaStreamWaitEvent(e->s_meta, e->ev_meta_fork, 0));
 		launch_meta(k, d_pcm, e->d_meta, e->d_blkflags, nb, e->s_meta);
@@ -301,14 +312,14 @@ static int run_stage_a(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	else if(raw) launch_meta(k, d_pcm, e->d_meta, e->d_blkflags, nb, st);  // no planar copy: the fast kernels read the caller's PCM
 	else launch_prep(k, d_pcm, e->d_sig, e->d_meta, e->d_blkflags, nb, st);
 	prof_mark(e, FB200_PROF_PREP, st);
-	e->launches++;
+	if(!fused) e->launches++;
 	if(k.nwin > 0) {
-		if(raw) launch_autoc4(k, d_pcm, overlap ? nullptr : e->d_meta, g.d_secwin, bs_plus_slack(k.bs), g.d_secs, e->d_autoc, nitems, st);
+		if(raw) launch_autoc4(k, d_pcm, (overlap || fused) ? nullptr : e->d_meta, g.d_secwin, bs_plus_slack(k.bs), g.d_secs, e->d_autoc, nitems, fused ? e->d_sigor : nullptr, g.or_sec, st);
 		else if(e->use_v1) launch_autoc_general(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		else launch_autoc3(k, e->d_sig, e->d_meta, g.d_windows, g.d_secs, e->d_autoc, nitems, st);
 		prof_mark(e, FB200_PROF_AUTOC, st);
 		if(overlap) FB_CUDA(cudaStreamWaitEvent(st, e->ev_meta_done, 0));
-		launch_lpc(k, e->d_autoc, g.d_cands, e->d_meta, e->d_cdesc, nitems, overlap ? 1 : 0, st);
+		launch_lpc(k, e->d_autoc, g.d_cands, e->d_meta, fused ? e->d_sigor : nullptr, e->d_cdesc, nitems, (overlap || fused) ? 1 : 0, st);
 		prof_mark(e, FB200_PROF_LPC, st);
 		e->launches += 2;
 	}
@@ -330,6 +341,17 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 	prof_mark(e, -1, st);
 	if(g.fast_search3 && !e->use_v1 && !(e->debug_path & 2)) launch_search5(k, g.fast_search3, g.maxord_t, g.search_wps, g.search5_smem, d_pcm, e->d_meta, e->d_cdesc, e->d_plans, nb, st);
 	else launch_search_general(k, g.search_smem, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems, st);
+	if(k.limit_min_bitrate && k.channels > 1 && !k.dis_const) {
+		// stream_encoder.c:3874-3879: blocks whose channels 0 .. n-2 all came out constant search their last channel (and mid /
+		// side) again with constant subframes disabled
+		launch_minbr_flags(k, e->d_plans, k.loose_ms ? e->d_blkflags : nullptr, nb, e->d_redo, st);
+		EncK k2 = k;
+		k2.dis_const = 1;
+		k2.redo = e->d_redo;
+		if(g.fast_search3 && !e->use_v1 && !(e->debug_path & 2)) launch_search5(k2, g.fast_search3, g.maxord_t, g.search_wps, g.search5_smem, d_pcm, e->d_meta, e->d_cdesc, e->d_plans, nb, st);
+		else launch_search_general(k2, g.search_smem, e->d_sig, e->d_meta, e->d_cdesc, e->d_plans, nitems, st);
+		e->launches += 2;
+	}
 	prof_mark(e, FB200_PROF_SEARCH, st);
 	if(g.emit3_rt && !e->use_v1 && !(e->debug_path & 4) && ((uintptr_t)d_pcm & 15) == 0) {
 		if((++e->epoch & kLbEpochMask) == 0) {
@@ -545,7 +567,6 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	// ---- engine scope (fail loudly, no fallback)
 	if(c.max_residual_partition_order > (uint32_t)kMaxPartitionOrder) { set_error("max_residual_partition_order %u > %d unsupported", c.max_residual_partition_order, kMaxPartitionOrder); return FB200_ERR_UNSUPPORTED; }
 	if(c.do_qlp_coeff_prec_search) { set_error("qlp coeff precision search unsupported"); return FB200_ERR_UNSUPPORTED; }
-	if(c.limit_min_bitrate) { set_error("limit_min_bitrate unsupported"); return FB200_ERR_UNSUPPORTED; }
 	if(c.num_apodizations == 0 || c.num_apodizations > FB200_MAX_APODIZATIONS) { set_error("invalid number of apodizations"); return FB200_ERR_INVALID; }
 	for(uint32_t a = 0; a < c.num_apodizations; a++)
 		if(c.apodizations[a].type < FB200_APOD_TUKEY || c.apodizations[a].type > FB200_APOD_WELCH) { set_error("apodization type %d unknown", c.apodizations[a].type); return FB200_ERR_INVALID; }
@@ -593,6 +614,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	for(int b = 0; b < 2; b++) {
 		ALLOC(e->ws[b].d_sig, (nitems * bs_stride + 1024) * sizeof(int32_t));  // + slack: k_autoc2 reads whole int4 bodies past the last run
 		ALLOC(e->ws[b].d_meta, nitems * sizeof(SigMeta));
+		ALLOC(e->ws[b].d_sigor, nitems * sizeof(uint32_t));
 		ALLOC(e->ws[b].d_blkflags, nb * sizeof(int));
 		ALLOC(e->ws[b].d_autoc, (e->max_nsec ? e->max_nsec : 1) * nitems * e->lag_stride * sizeof(double));
 		ALLOC(e->ws[b].d_cdesc, (e->max_nslots ? e->max_nslots : 1) * nitems * sizeof(CandDesc));
@@ -607,6 +629,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	ALLOC(e->d_lookback, nb * sizeof(unsigned long long));
 	ALLOC(e->d_ticket, sizeof(unsigned));
 	ALLOC(e->d_err, sizeof(int));
+	ALLOC(e->d_redo, nb * sizeof(int));
 #undef ALLOC
 	if(cudaStreamCreateWithFlags(&e->s_a, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&e->s_meta, cudaStreamNonBlocking) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_meta_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_meta_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -673,7 +696,7 @@ void fb200_encoder_destroy(fb200_encoder *e)
 		cudaFree(kv.second.d_windows); cudaFree(kv.second.d_secs); cudaFree(kv.second.d_cands); cudaFree(kv.second.d_secwin);
 	}
 	for(int b = 0; b < 2; b++) {
-		cudaFree(e->ws[b].d_sig); cudaFree(e->ws[b].d_meta); cudaFree(e->ws[b].d_blkflags); cudaFree(e->ws[b].d_autoc); cudaFree(e->ws[b].d_cdesc);
+		cudaFree(e->ws[b].d_sig); cudaFree(e->ws[b].d_meta); cudaFree(e->ws[b].d_sigor); cudaFree(e->ws[b].d_blkflags); cudaFree(e->ws[b].d_autoc); cudaFree(e->ws[b].d_cdesc);
 		if(e->ev_a[b]) cudaEventDestroy(e->ev_a[b]);
 		if(e->ev_b[b]) cudaEventDestroy(e->ev_b[b]);
 	}
@@ -683,7 +706,7 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	if(e->ev_meta_fork) cudaEventDestroy(e->ev_meta_fork);
 	if(e->ev_meta_done) cudaEventDestroy(e->ev_meta_done);
 	cudaFree(e->d_plans); cudaFree(e->d_slots); cudaFree(e->d_frame_bytes); cudaFree(e->d_chan_assign);
-	cudaFree(e->d_running); cudaFree(e->d_err);
+	cudaFree(e->d_running); cudaFree(e->d_err); cudaFree(e->d_redo);
 	cudaFree(e->d_crc_tab); cudaFree(e->d_lookback); cudaFree(e->d_ticket);
 	cudaFree(e->d_pcm); cudaFree(e->d_packed); cudaFree(e->d_out); cudaFree(e->d_offsets);
 	if(e->stream) cudaStreamDestroy(e->stream);

@@ -102,6 +102,8 @@ struct EncK {
 	uint32_t blk0;         // index (inside the call) of this launch's first block
 	int f64b;            // k_search5: the second warp of a signal evaluates its candidates on the FP64 pipe
 	int file_blocks;     // > 0: frame numbers restart every file_blocks blocks (many-file batches: one stream per file, stream_encoder.c:3772)
+	int limit_min_bitrate;  // stream_encoder.c:3874: a frame must not consist of constant subframes only
+	const int *redo;     // search kernels, second pass of limit_min_bitrate: only blocks with redo[blk] != 0, only signals >= channels - 1
 };
 
 // ---- row layout shared by k_search5 and k_emit3: a signal lives in rows of R_T samples with a 36-word stride and one
@@ -166,7 +168,8 @@ void launch_unpack(const void *packed, int bytes_per_sample, int32_t *pcm, unsig
 void launch_meta(const EncK &k, const int32_t *pcm, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
 void launch_prep(const EncK &k, const int32_t *pcm, int32_t *sig, SigMeta *meta, int *blkflags, int nb, cudaStream_t st);
 void launch_autoc_general(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
-void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, int autoc_unshifted, cudaStream_t st);
+void launch_minbr_flags(const EncK &k, const SubframePlan *plans, const int *blkflags, int nb, int *flags, cudaStream_t st);
+void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, SigMeta *meta, const uint32_t *sigor, CandDesc *cdesc, int nitems, int autoc_unshifted, cudaStream_t st);
 void launch_search_general(const EncK &k, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st);
 void launch_emit_general(const EncK &k, size_t smem, const int32_t *sig, const int *blkflags, const SubframePlan *plans, uint8_t *slots, uint32_t *frame_bytes, uint32_t *chan_assign, int nb, cudaStream_t st);
 void launch_scan(const uint32_t *bytes, int n, unsigned long long *offsets, unsigned long long *running, cudaStream_t st);
@@ -176,7 +179,7 @@ void general_kernels_init(int device);  // raises the dynamic shared-memory limi
 // autoc_kernel.cu
 void launch_autoc3(const EncK &k, const int32_t *sig, const SigMeta *meta, const float *windows, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
 void autoc3_init(int device);
-void launch_autoc4(const EncK &k, const int32_t *pcm, const SigMeta *meta, const float *secwin, int secwin_stride, const DevSection *secs, double *autoc, int nitems, cudaStream_t st);
+void launch_autoc4(const EncK &k, const int32_t *pcm, const SigMeta *meta, const float *secwin, int secwin_stride, const DevSection *secs, double *autoc, int nitems, uint32_t *sigor, int or_sec, cudaStream_t st);
 void autoc4_init(int device);
 constexpr int kSecwinSlack = 160;  // zero floats behind every per-section weight table (>= the largest autocorrelation tile)
 // search_kernel.cu

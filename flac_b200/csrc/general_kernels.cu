@@ -38,12 +38,17 @@ void launch_autoc_general(const EncK &k, const int32_t *sig, const SigMeta *meta
 	else autoc_general<33>(k, sig, meta, windows, secs, autoc, nitems, st);
 }
 
-void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, const SigMeta *meta, CandDesc *cdesc, int nitems, int autoc_unshifted, cudaStream_t st)
+void launch_minbr_flags(const EncK &k, const SubframePlan *plans, const int *blkflags, int nb, int *flags, cudaStream_t st)
+{
+	k_minbr_flags<<<(nb + 127) / 128, 128, 0, st>>>(k, plans, blkflags, nb, flags);
+}
+
+void launch_lpc(const EncK &k, const double *autoc, const DevCand *cands, SigMeta *meta, const uint32_t *sigor, CandDesc *cdesc, int nitems, int autoc_unshifted, cudaStream_t st)
 {
 	const int total = nitems * k.nwin;
-	if(k.max_order <= 8) k_lpc<8><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems, autoc_unshifted);
-	else if(k.max_order <= 12) k_lpc<12><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems, autoc_unshifted);
-	else k_lpc<32><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, cdesc, nitems, autoc_unshifted);
+	if(k.max_order <= 8) k_lpc<8><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, sigor, cdesc, nitems, autoc_unshifted);
+	else if(k.max_order <= 12) k_lpc<12><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, sigor, cdesc, nitems, autoc_unshifted);
+	else k_lpc<32><<<(total + 127) / 128, 128, 0, st>>>(k, autoc, cands, meta, sigor, cdesc, nitems, autoc_unshifted);
 }
 
 void launch_search_general(const EncK &k, size_t smem, const int32_t *sig, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nitems, cudaStream_t st)

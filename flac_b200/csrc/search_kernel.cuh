@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int tid = threadIdx.x, NT = blockDim.x, warp = tid >> 5, lane = tid & 31, bs = P.bs, nsig = P.nsig, ch = P.channels;
 	const int blk = blockIdx.x;
+	if(P.redo && !P.redo[blk]) return;  // second pass of limit_min_bitrate: flagged blocks only
 	const int nrows = bs / R_T;
 	const int slice_words = kSearch4ZeroRow + nrows * 36;
 	int32_t *const slices = reinterpret_cast<int32_t *>(smem_raw);
@@ -269,8 +270,9 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 	// ---- this warp's signal and role
 	const int sidx = warp / WPS, part = warp - sidx * WPS;
 	const bool have_signal = sidx < nsig;
+	const bool skip_sig = P.redo != nullptr && sidx < ch - 1;  // second pass: these signals keep their plan
 	const SigMeta M = have_signal ? bm[sidx] : SigMeta{0, 0};
-	const bool active = have_signal && M.bps != 0;
+	const bool active = have_signal && M.bps != 0 && !skip_sig;
 	const int32_t *const xs = slices + (have_signal ? sidx : 0) * slice_words + kSearch4ZeroRow;
 	unsigned char *const my_scratch = scratch0 + (size_t)(have_signal ? warp : 0) * scratch_bytes;
 	unsigned long long *const leaf = reinterpret_cast<unsigned long long *>(my_scratch);
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 		for(int j = 0; j < MAXORD; j++) Rz.q[j] = b_q[j];
 	}
 	__syncthreads();
-	if(!have_signal || part != 0) return;
+	if(!have_signal || part != 0 || skip_sig) return;
 	SubframePlan *plan = plans + (size_t)blk * nsig + sidx;
 	if(!active) {
 		if(lane == 0) { plan->type = -1; plan->est_bits = 0xffffffffu; }

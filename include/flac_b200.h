@@ -92,7 +92,7 @@ typedef struct {
 	int32_t disable_constant_subframes;     /* FLAC__stream_encoder_disable_constant_subframes (share/private.h:41) */
 	int32_t disable_fixed_subframes;        /* ..._disable_fixed_subframes */
 	int32_t disable_verbatim_subframes;     /* ..._disable_verbatim_subframes */
-	int32_t limit_min_bitrate;              /* set_limit_min_bitrate (1 -> FB200_ERR_UNSUPPORTED) */
+	int32_t limit_min_bitrate;              /* set_limit_min_bitrate (stream_encoder.c:3874) */
 } fb200_encoder_config;
 
 typedef struct fb200_encoder fb200_encoder;

@@ -233,3 +233,25 @@ def test_file_blocks_restarts_frame_numbers(ch, bps, level):
     for f in range(files):
         want += _oracle_frames(x[f * per_file * 4096:(f + 1) * per_file * 4096], bps, 44100, level)
     _assert_same(got, want, "file-major frame numbering")
+
+
+@pytest.mark.parametrize("ch,bps,level,bs", [(2, 16, 5, 0), (2, 16, 8, 0), (2, 16, 0, 0), (2, 16, 1, 0), (1, 16, 5, 0), (3, 20, 5, 0),
+                                            (8, 24, 8, 0), (2, 24, 5, 0), (2, 16, 5, 1000), (2, 16, 2, 4608)])
+def test_limit_min_bitrate(ch, bps, level, bs):
+    """stream_encoder.c:3874-3879: a frame must not consist of constant subframes only -- blocks of digital silence, of a DC
+    level, with one constant and one live channel, and ordinary audio, against the oracle and the compiled reference."""
+    blk = bs or 4096
+    x = signals.music_like(blk * 8 + 311, ch, bps, 44100, seed=23)
+    x[blk:2 * blk] = 0                       # silence: every channel constant
+    x[2 * blk:3 * blk] = 37                  # DC: constant, non-zero (mid constant, side zero)
+    x[3 * blk:4 * blk, 0] = -5               # first channel constant, the others live
+    x[4 * blk:5 * blk, ch - 1] = 9           # last channel constant, the others live
+    x[6 * blk:7 * blk] = np.arange(ch)[None, :] * 3   # every channel its own constant
+    got = _gpu_frames(x, bps, 44100, level, bs, limit_min_bitrate=1)
+    _assert_same(got, _oracle_frames(x, bps, 44100, level, bs, limit_min_bitrate=1), "oracle")
+    plain = _gpu_frames(x, bps, 44100, level, bs)
+    if level != 1:  # loose mid-side: the constant frames are coded mid/side only, outside the independent-channel loop
+        assert plain != got, "limit_min_bitrate changed nothing"
+    if reflib.available("default"):
+        _, _, ref = reflib.encode(x, bps, rate=44100, level=level, blocksize=bs, opts=reflib.RefEncOpts(limit_min_bitrate=1))
+        _assert_same(got, ref, "reference[default]")
