@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 	else {
 		// lpc.c:1608-1630 FLAC__lpc_compute_best_order
 		const uint32_t total_samples = (uint32_t)P.bs;
-		const uint32_t overhead = (uint32_t)(sbps + P.qlp_precision);
+		const uint32_t overhead = (uint32_t)(sbps + (P.prec_search ? (int)kMinQlpPrecision : P.qlp_precision));  // stream_encoder.c:4385-4389
 		const double error_scale = 0.5 / (double)total_samples;
 		int best_index = 0;
 		double best_bits = (double)0xffffffffu;
@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 			}
 		lo = hi = best_index + 1;
 	}
+	const int nprec = P.prec_search ? kQlpPrecisionSteps : 1;
 	for(int order = lo; order <= hi; order++) {
-		CandDesc &D = slots[order - lo];
 		double err_o = 0.0;
 #pragma unroll
 		for(int i = 0; i < MO; i++)
@@ -434,10 +434,20 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 		// stream_encoder.c:4227-4229 "don't even try"
 		const double lbps = expected_bits_scale(err_o, 0.5 / (double)(uint32_t)(P.bs - order));
 		if(lbps >= (double)sbps) continue;
-		int precision = P.qlp_precision;
-		if(sbps <= 17) precision = min(precision, 32 - sbps - (int)ilog2_u32((uint32_t)order));  // :4591-4595
+		// precisions tried for this order (:4230-4243): the configured one, or 5 .. 15 (<= 17-bit subframes: capped so that the
+		// decoder's 32-bit arithmetic suffices)
+		int minp = P.qlp_precision, maxp = P.qlp_precision;
+		if(P.prec_search) {
+			minp = (int)kMinQlpPrecision;
+			maxp = (int)kMaxQlpPrecision;
+			if(sbps <= 17) maxp = max(min(32 - sbps - (int)ilog2_u32((uint32_t)order), (int)kMaxQlpPrecision), minp);
+		}
 		double scratch_err[MO];
 		(void)levinson<MO>(ac, order, order, scratch_err, coef);
+		for(int prec_try = minp; prec_try <= maxp; prec_try++) {
+		CandDesc &D = slots[(order - lo) * nprec + (prec_try - minp)];
+		int precision = prec_try;
+		if(sbps <= 17) precision = min(precision, 32 - sbps - (int)ilog2_u32((uint32_t)order));  // :4591-4595
 		int q[MO], shift;
 #pragma unroll
 		for(int i = 0; i < MO; i++) q[i] = 0;
@@ -458,6 +468,7 @@ __global__ void __launch_bounds__(128) k_lpc(EncK P, const double *__restrict__ 
 #pragma unroll
 		for(int i = 0; i < FB200_MAX_LPC_ORDER; i++) D.qlp[i] = (i < MO && i < order) ? q[i < MO ? i : 0] : 0;
 		D.valid = 1;
+		}
 	}
 }
 

@@ -170,6 +170,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 	k.lags = k.max_order + 1;
 	k.lag_stride = (int)e->lag_stride;
 	k.qlp_precision = (int)c.qlp_coeff_precision;
+	k.prec_search = c.do_qlp_coeff_prec_search ? 1 : 0;
 	k.exhaustive = c.do_exhaustive_model_search;
 	{   // stream_encoder.c:3759-3761, format.c:540-548
 		int o = 0, b = bs;
@@ -223,7 +224,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 	k.nsec = (int)secs.size();
 	g.or_sec = secs.empty() ? -1 : 0;  // every apodization opens with its full-length section
 	k.nwin = (int)cands.size();
-	k.nslots = k.nwin * (k.exhaustive ? (k.max_order > 0 ? k.max_order : 1) : 1);
+	k.nslots = k.nwin * (k.exhaustive ? (k.max_order > 0 ? k.max_order : 1) : 1) * (k.prec_search ? kQlpPrecisionSteps : 1);
 	if((size_t)k.nsec > e->max_nsec || (size_t)k.nslots > e->max_nslots) {
 		set_error("internal: geometry for blocksize %d exceeds workspace (nsec %d/%zu nslots %d/%zu)", bs, k.nsec, e->max_nsec, k.nslots, e->max_nslots);
 		return FB200_ERR_INVALID;
@@ -566,7 +567,6 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	if(c.min_residual_partition_order >= c.max_residual_partition_order) c.min_residual_partition_order = c.max_residual_partition_order;
 	// ---- engine scope (fail loudly, no fallback)
 	if(c.max_residual_partition_order > (uint32_t)kMaxPartitionOrder) { set_error("max_residual_partition_order %u > %d unsupported", c.max_residual_partition_order, kMaxPartitionOrder); return FB200_ERR_UNSUPPORTED; }
-	if(c.do_qlp_coeff_prec_search) { set_error("qlp coeff precision search unsupported"); return FB200_ERR_UNSUPPORTED; }
 	if(c.num_apodizations == 0 || c.num_apodizations > FB200_MAX_APODIZATIONS) { set_error("invalid number of apodizations"); return FB200_ERR_INVALID; }
 	for(uint32_t a = 0; a < c.num_apodizations; a++)
 		if(c.apodizations[a].type < FB200_APOD_TUKEY || c.apodizations[a].type > FB200_APOD_WELCH) { set_error("apodization type %d unknown", c.apodizations[a].type); return FB200_ERR_INVALID; }
@@ -598,7 +598,7 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 				}
 		}
 		e->max_nsec = nsec;
-		e->max_nslots = nwin * (c.do_exhaustive_model_search ? (c.max_lpc_order ? c.max_lpc_order : 1) : 1);
+		e->max_nslots = nwin * (c.do_exhaustive_model_search ? (c.max_lpc_order ? c.max_lpc_order : 1) : 1) * (c.do_qlp_coeff_prec_search ? kQlpPrecisionSteps : 1);
 	}
 	const size_t nb = e->max_blocks, nitems = nb * e->nsig;
 	const size_t bs_stride = (size_t)round_up((int)c.blocksize, 4);

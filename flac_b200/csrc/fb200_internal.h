@@ -31,6 +31,7 @@ constexpr uint32_t kRiceParamLen = 4, kRice2ParamLen = 5;
 constexpr uint32_t kRiceEscape = 15, kRice2Escape = 31;
 constexpr uint32_t kMaxFixedOrder = 4;
 constexpr uint32_t kMinQlpPrecision = 5, kMaxQlpPrecision = 15;
+constexpr int kQlpPrecisionSteps = 11;  // precisions a precision search tries per order: 5 .. 15
 constexpr uint32_t kMaxExtraResidualBps = 4;  // private/stream_encoder.h:44
 constexpr int kMaxPartitionOrder = 8;         // engine scope (-0..-8 use <= 6)
 constexpr int kMaxPartitions = 1 << kMaxPartitionOrder;
@@ -91,6 +92,7 @@ struct EncK {
 	int lags;            // max_order + 1
 	int lag_stride;      // doubles per (section,item) autocorrelation record
 	int qlp_precision, exhaustive;
+	int prec_search;     // do_qlp_coeff_prec_search: every order is tried at precisions 5 .. 15 (stream_encoder.c:4230-4243)
 	int min_po, max_po;  // resolved for this blocksize (stream_encoder.c:3759-3761)
 	int rice_limit;      // 15 (stream bps <= 16) or 31 (stream_encoder.c:4076)
 	int dis_const, dis_fixed, dis_verb;

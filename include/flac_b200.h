@@ -83,7 +83,7 @@ typedef struct {
 	int32_t loose_mid_side_stereo;          /* set_loose_mid_side_stereo */
 	uint32_t max_lpc_order;                 /* set_max_lpc_order      0..32 */
 	uint32_t qlp_coeff_precision;           /* set_qlp_coeff_precision 0 = reference default */
-	int32_t do_qlp_coeff_prec_search;       /* set_do_qlp_coeff_prec_search (1 -> FB200_ERR_UNSUPPORTED) */
+	int32_t do_qlp_coeff_prec_search;       /* set_do_qlp_coeff_prec_search (flac -p; stream_encoder.c:4230-4243) */
 	int32_t do_exhaustive_model_search;     /* set_do_exhaustive_model_search */
 	uint32_t min_residual_partition_order;  /* set_min_residual_partition_order */
 	uint32_t max_residual_partition_order;  /* set_max_residual_partition_order (<= 8) */

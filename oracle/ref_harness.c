@@ -65,6 +65,7 @@ typedef struct {
 	int32_t disable_isa;     /* value for FLAC__stream_encoder_disable_instruction_set, 0 none */
 	int32_t streamable_subset; /* -1 keep, 0/1 */
 	int32_t limit_min_bitrate; /* -1 keep, 0/1 */
+	int32_t prec_search;     /* -1 keep, 0/1: do_qlp_coeff_prec_search */
 	const char *apodization; /* NULL keep */
 } ref_enc_opts;
 
@@ -109,6 +110,7 @@ int ref_encode(const int32_t *interleaved, uint64_t samples_per_channel,
 		if(opts->disable_isa > 0) FLAC__stream_encoder_disable_instruction_set(e, opts->disable_isa);
 		if(opts->streamable_subset >= 0) FLAC__stream_encoder_set_streamable_subset(e, opts->streamable_subset);
 		if(opts->limit_min_bitrate >= 0) FLAC__stream_encoder_set_limit_min_bitrate(e, opts->limit_min_bitrate);
+		if(opts->prec_search >= 0) FLAC__stream_encoder_set_do_qlp_coeff_prec_search(e, opts->prec_search);
 		if(opts->apodization) FLAC__stream_encoder_set_apodization(e, opts->apodization);
 	}
 

@@ -14,11 +14,11 @@ class RefEncOpts(C.Structure):
         ("exhaustive", C.c_int32), ("mid_side", C.c_int32), ("loose_mid_side", C.c_int32),
         ("max_lpc_order", C.c_int32), ("qlp_precision", C.c_int32), ("min_part_order", C.c_int32),
         ("max_part_order", C.c_int32), ("disable_isa", C.c_int32), ("streamable_subset", C.c_int32),
-        ("limit_min_bitrate", C.c_int32), ("apodization", C.c_char_p),
+        ("limit_min_bitrate", C.c_int32), ("prec_search", C.c_int32), ("apodization", C.c_char_p),
     ]
 
     def __init__(self, **kw):
-        super().__init__(-1, -1, -1, -1, -1, -1, -1, 0, -1, -1, None)
+        super().__init__(-1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1, None)
         for k, v in kw.items():
             if k == "apodization" and isinstance(v, str):
                 v = v.encode()

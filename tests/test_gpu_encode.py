@@ -255,3 +255,18 @@ def test_limit_min_bitrate(ch, bps, level, bs):
     if reflib.available("default"):
         _, _, ref = reflib.encode(x, bps, rate=44100, level=level, blocksize=bs, opts=reflib.RefEncOpts(limit_min_bitrate=1))
         _assert_same(got, ref, "reference[default]")
+
+
+@pytest.mark.parametrize("ch,bps,level,bs,exhaustive", [(2, 16, 5, 0, 0), (2, 16, 8, 0, 0), (2, 24, 5, 0, 0), (1, 16, 3, 0, 0), (2, 16, 5, 1152, 1),
+                                                       (8, 24, 8, 0, 0), (2, 16, 5, 1000, 0), (2, 20, 8, 4608, 0)])
+def test_qlp_coeff_precision_search(ch, bps, level, bs, exhaustive):
+    """flac -p (stream_encoder.c:4230-4243): every order is quantised at precisions 5 .. 15, in the reference's evaluation order."""
+    x = signals.music_like((bs or 4096) * 3 + 311, ch, bps, 44100, seed=29)
+    kw = dict(do_qlp_coeff_prec_search=1, do_exhaustive_model_search=exhaustive)
+    got = _gpu_frames(x, bps, 44100, level, bs, **kw)
+    _assert_same(got, _oracle_frames(x, bps, 44100, level, bs, **kw), "oracle")
+    assert got != _gpu_frames(x, bps, 44100, level, bs, do_exhaustive_model_search=exhaustive), "precision search changed nothing"
+    if reflib.available("default"):
+        opts = reflib.RefEncOpts(prec_search=1, exhaustive=exhaustive if exhaustive else -1)
+        _, _, ref = reflib.encode(x, bps, rate=44100, level=level, blocksize=bs, opts=opts, variant="strict")
+        _assert_same(got, ref, "reference[strict]")

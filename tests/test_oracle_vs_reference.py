@@ -97,6 +97,8 @@ def test_option_matrix():
         (dict(qlp_precision=9), dict(qlp_coeff_precision=9), 5),
         (dict(min_part_order=2, max_part_order=8), dict(min_residual_partition_order=2, max_residual_partition_order=8), 5),
         (dict(limit_min_bitrate=1), dict(limit_min_bitrate=1), 5),
+        (dict(prec_search=1), dict(do_qlp_coeff_prec_search=1), 5),
+        (dict(prec_search=1), dict(do_qlp_coeff_prec_search=1), 8),
     ]
     for ref_kw, cfg_kw, level in cases:
         bad, _, _ = _frames_equal(x, 16, 44100, level, opts=reflib.RefEncOpts(**ref_kw), **cfg_kw)
