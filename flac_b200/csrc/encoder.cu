@@ -84,6 +84,13 @@ struct fb200_encoder {
 	// s_a concurrently with stage B (search/emit/scan/gather) of sub-batch i on the caller's stream
 	struct WS { int32_t *d_sig; SigMeta *d_meta; int *d_blkflags; double *d_autoc; CandDesc *d_cdesc; uint32_t *d_sigor; } ws[2] = {};
 	cudaStream_t s_a = nullptr, s_meta = nullptr;
+	// slice mode (the call's blocks fit the workspace): every chunk owns its slice of workspace set 0, so the stage A's of
+	// different chunks are independent and rotate over these streams (s_as[0] == s_a) -- the latency-bound autocorrelation of
+	// a small chunk no longer serialises the pipeline
+	static constexpr int kStageAStreams = 4;
+	cudaStream_t s_as[kStageAStreams] = {};
+	bool slice_mode = false;
+	std::vector<cudaEvent_t> ev_ca;  // per chunk: stage A done
 	cudaEvent_t ev_meta_fork = nullptr, ev_meta_done = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
 	bool ev_b_valid[2] = {false, false};
@@ -284,10 +291,16 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 
 static int bs_plus_slack(int bs) { return bs + kSecwinSlack; }
 
-static void use_ws(fb200_encoder *e, int b)
+// workspace set b, starting at block `off_blocks` of it (every array is laid out per block / per (block, signal) item, sized
+// for max_blocks blocks with the stream's largest section / slot counts: a launch of n blocks at offset o stays inside)
+static void use_ws(fb200_encoder *e, int b, size_t off_blocks = 0)
 {
-	e->d_sig = e->ws[b].d_sig; e->d_meta = e->ws[b].d_meta; e->d_blkflags = e->ws[b].d_blkflags; e->d_sigor = e->ws[b].d_sigor;
-	e->d_autoc = e->ws[b].d_autoc; e->d_cdesc = e->ws[b].d_cdesc;
+	const size_t oi = off_blocks * (size_t)e->nsig;
+	const size_t bs_stride = (size_t)round_up((int)e->cfg.blocksize, 4);
+	e->d_sig = e->ws[b].d_sig + oi * bs_stride; e->d_meta = e->ws[b].d_meta + oi; e->d_blkflags = e->ws[b].d_blkflags + off_blocks;
+	e->d_sigor = e->ws[b].d_sigor + oi;
+	e->d_autoc = e->ws[b].d_autoc + oi * (e->max_nsec ? e->max_nsec : 1) * e->lag_stride;
+	e->d_cdesc = e->ws[b].d_cdesc + oi * (e->max_nslots ? e->max_nslots : 1);
 }
 
 // Stage A of nb blocks of size g.bs starting at d_pcm: k_prep, k_autoc, k_lpc (writes the current workspace set).
@@ -386,24 +399,47 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 
 struct PipeChunk { uint64_t first; uint32_t nb; uint32_t blocksize; cudaEvent_t wait_before_a; };
 
-// Enqueue chunk `idx` of a call: stage A on e->s_a, stage B on `sb`; consecutive chunks alternate workspace sets.
+// Enqueue chunk `idx` of a call: stage A on a stage-A stream, stage B on `sb`. Slice mode: the chunk works in its own slice of
+// workspace set 0; otherwise consecutive chunks alternate between the two sets and wait for the set's previous user.
+static cudaStream_t stage_a_stream(fb200_encoder *e, size_t idx) { return e->slice_mode ? e->s_as[idx % fb200_encoder::kStageAStreams] : e->s_a; }
+
 static int enqueue_chunk(fb200_encoder *e, size_t idx, const PipeChunk &c, const int32_t *d_pcm_base, uint32_t first_frame_number,
                          uint8_t *d_out, size_t out_cap, unsigned long long *d_offsets, cudaStream_t sb)
 {
 	const uint32_t bs = e->cfg.blocksize, ch = e->cfg.channels;
-	const int b = (int)(idx & 1);
+	const int b = e->slice_mode ? 0 : (int)(idx & 1);
+	cudaStream_t sa = stage_a_stream(e, idx);
 	Geometry *g = nullptr;
 	int rc;
 	if((rc = build_geometry(e, (int)c.blocksize, &g)) != FB200_OK) return rc;
-	if(c.wait_before_a) FB_CUDA(cudaStreamWaitEvent(e->s_a, c.wait_before_a, 0));
-	if(e->ev_b_valid[b]) FB_CUDA(cudaStreamWaitEvent(e->s_a, e->ev_b[b], 0));  // stage B two chunks ago is done with this set
-	use_ws(e, b);
-	if((rc = run_stage_a(e, *g, d_pcm_base + (size_t)c.first * bs * ch, (int)c.nb, e->s_a)) != FB200_OK) return rc;
-	FB_CUDA(cudaEventRecord(e->ev_a[b], e->s_a));
-	FB_CUDA(cudaStreamWaitEvent(sb, e->ev_a[b], 0));
+	if(c.wait_before_a) FB_CUDA(cudaStreamWaitEvent(sa, c.wait_before_a, 0));
+	if(!e->slice_mode && e->ev_b_valid[b]) FB_CUDA(cudaStreamWaitEvent(sa, e->ev_b[b], 0));  // stage B two chunks ago is done with this set
+	use_ws(e, b, e->slice_mode ? (size_t)c.first : 0);
+	if((rc = run_stage_a(e, *g, d_pcm_base + (size_t)c.first * bs * ch, (int)c.nb, sa)) != FB200_OK) return rc;
+	cudaEvent_t done_a = e->ev_a[b];
+	if(e->slice_mode) {
+		while(e->ev_ca.size() <= idx) {
+			cudaEvent_t ev;
+			FB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			e->ev_ca.push_back(ev);
+		}
+		done_a = e->ev_ca[idx];
+	}
+	FB_CUDA(cudaEventRecord(done_a, sa));
+	FB_CUDA(cudaStreamWaitEvent(sb, done_a, 0));
 	if((rc = run_stage_b(e, *g, d_pcm_base + (size_t)c.first * bs * ch, (int)c.nb, first_frame_number, c.first, d_out, out_cap, d_offsets, sb)) != FB200_OK) return rc;
-	FB_CUDA(cudaEventRecord(e->ev_b[b], sb));
-	e->ev_b_valid[b] = true;
+	if(!e->slice_mode) {
+		FB_CUDA(cudaEventRecord(e->ev_b[b], sb));
+		e->ev_b_valid[b] = true;
+	}
+	return FB200_OK;
+}
+
+// after the call's set-up work was enqueued on `st`: every stage-A stream starts behind it
+static int fork_stage_a(fb200_encoder *e, cudaStream_t st)
+{
+	FB_CUDA(cudaEventRecord(e->ev_fork, st));
+	for(int i = 0; i < (e->slice_mode ? fb200_encoder::kStageAStreams : 1); i++) FB_CUDA(cudaStreamWaitEvent(e->s_as[i], e->ev_fork, 0));
 	return FB200_OK;
 }
 
@@ -631,7 +667,10 @@ int fb200_encoder_create(const fb200_encoder_config *cfg_in, int device, uint32_
 	ALLOC(e->d_err, sizeof(int));
 	ALLOC(e->d_redo, nb * sizeof(int));
 #undef ALLOC
-	if(cudaStreamCreateWithFlags(&e->s_a, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&e->s_meta, cudaStreamNonBlocking) != cudaSuccess ||
+	bool streams_ok = true;
+	for(int i = 0; i < fb200_encoder::kStageAStreams; i++) streams_ok = streams_ok && cudaStreamCreateWithFlags(&e->s_as[i], cudaStreamNonBlocking) == cudaSuccess;
+	e->s_a = e->s_as[0];
+	if(!streams_ok || cudaStreamCreateWithFlags(&e->s_meta, cudaStreamNonBlocking) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_meta_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_meta_done, cudaEventDisableTiming) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
 	   cudaEventCreateWithFlags(&e->ev_a[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_a[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -701,7 +740,8 @@ void fb200_encoder_destroy(fb200_encoder *e)
 		if(e->ev_b[b]) cudaEventDestroy(e->ev_b[b]);
 	}
 	if(e->ev_fork) cudaEventDestroy(e->ev_fork);
-	if(e->s_a) cudaStreamDestroy(e->s_a);
+	for(int i = 0; i < fb200_encoder::kStageAStreams; i++) if(e->s_as[i]) cudaStreamDestroy(e->s_as[i]);
+	for(cudaEvent_t ev : e->ev_ca) cudaEventDestroy(ev);
 	if(e->s_meta) cudaStreamDestroy(e->s_meta);
 	if(e->ev_meta_fork) cudaEventDestroy(e->ev_meta_fork);
 	if(e->ev_meta_done) cudaEventDestroy(e->ev_meta_done);
@@ -755,8 +795,8 @@ int fb200_encode_device(fb200_encoder *e, const int32_t *d_pcm, uint64_t samples
 	for(uint64_t done = 0; done < nfull; done += chunk)
 		chunks.push_back(PipeChunk{done, (uint32_t)((nfull - done) < chunk ? (nfull - done) : chunk), bs, nullptr});
 	if(tail) chunks.push_back(PipeChunk{nfull, 1, tail, nullptr});  // short last block: own windows / header blocksize (stream_encoder.c:1703-1711)
-	FB_CUDA(cudaEventRecord(e->ev_fork, st));
-	FB_CUDA(cudaStreamWaitEvent(e->s_a, e->ev_fork, 0));
+	e->slice_mode = nfull + (tail ? 1 : 0) <= e->max_blocks;
+	{ const int rc = fork_stage_a(e, st); if(rc != FB200_OK) return rc; }
 	e->ev_b_valid[0] = e->ev_b_valid[1] = false;
 	for(size_t i = 0; i < chunks.size(); i++) {
 		const int rc = enqueue_chunk(e, i, chunks[i], d_pcm, first_frame_number, d_out, out_capacity, offs, st);
@@ -844,6 +884,8 @@ static int encode_host_impl(fb200_encoder *e, const void *pcm_any, uint32_t byte
 	cudaStream_t sc = e->stream;
 	FB_CUDA(cudaMemsetAsync(e->d_running, 0, 2 * sizeof(unsigned long long), sc));
 	FB_CUDA(cudaMemsetAsync(e->d_err, 0, sizeof(int), sc));
+	e->slice_mode = nfr <= e->max_blocks;
+	{ const int rc = fork_stage_a(e, sc); if(rc != FB200_OK) return rc; }  // the error word is cleared before any kernel of this call may set it
 	e->ev_b_valid[0] = e->ev_b_valid[1] = false;
 	for(size_t ci = 0; ci < used; ci++) {
 		PipeChunk &c = chunks[ci];
@@ -853,11 +895,17 @@ static int encode_host_impl(fb200_encoder *e, const void *pcm_any, uint32_t byte
 		else {
 			// packed 16-/24-bit PCM crosses PCIe as it is; one unpack kernel widens it to the int32 layout the pipeline reads
 			FB_CUDA(cudaMemcpyAsync(e->d_packed + off_elems * bytes_per_sample, pcm_bytes_host + off_elems * bytes_per_sample, nsamp * ch * bytes_per_sample, cudaMemcpyHostToDevice, e->s_h2d));
-			launch_unpack(e->d_packed + off_elems * bytes_per_sample, (int)bytes_per_sample, e->d_pcm + off_elems, (unsigned long long)nsamp * ch, (int)e->cfg.bits_per_sample, e->d_err, e->s_h2d);
-			e->launches++;
 		}
 		FB_CUDA(cudaEventRecord(e->ev_h2d[ci], e->s_h2d));
 		c.wait_before_a = e->ev_h2d[ci];
+		if(packed) {
+			// the unpack kernel runs on the compute stream, so the copy stream carries nothing but copies (back to back)
+			cudaStream_t sa = stage_a_stream(e, ci);
+			FB_CUDA(cudaStreamWaitEvent(sa, e->ev_h2d[ci], 0));
+			launch_unpack(e->d_packed + off_elems * bytes_per_sample, (int)bytes_per_sample, e->d_pcm + off_elems, (unsigned long long)nsamp * ch, (int)e->cfg.bits_per_sample, e->d_err, sa);
+			e->launches++;
+			c.wait_before_a = nullptr;
+		}
 		const int rc = enqueue_chunk(e, ci, c, e->d_pcm, first_frame_number, e->d_out, e->d_out_cap, e->d_offsets, sc);
 		if(rc != FB200_OK) return rc;
 		FB_CUDA(cudaMemcpyAsync(&e->h_totals[ci], e->d_running + e->run_cur, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));

@@ -1,4 +1,4 @@
-"""End-to-end (host buffers through fb200_encode_host) step time against the number of copy/compute
+"""End-to-end (packed 16-bit host buffers through fb200_encode_host_packed) step time against the number of copy/compute
 chunks per call (FB200_HOST_CHUNKS). Prints one line per (workload, chunks).
     python tools/sweep_host_chunks.py [chunks ...]"""
 import os
@@ -18,8 +18,10 @@ CHUNKS = [int(a) for a in sys.argv[1:]] or [3, 5, 8, 12, 16, 24]
 for name, (ch, bps, rate, level) in {"cfg2": (2, 16, 44100, 5), "cfg2_l8": (2, 16, 44100, 8)}.items():
     blocks, bs = 10000, 4096
     x = bench.make_pcm(ch, bps, rate, blocks, bs, seed=1)
-    h_pcm = torch.empty(x.shape, dtype=torch.int32, pin_memory=True)
-    h_pcm.numpy()[:] = x
+    pk = flac_b200.pack_pcm(x, 2)
+    h_pcm = torch.empty(pk.shape, dtype=torch.uint8, pin_memory=True)
+    h_pcm.numpy()[:] = pk
+    ns = x.shape[0]
     for nchunks in CHUNKS:
         os.environ["FB200_HOST_CHUNKS"] = str(nchunks)
         enc = flac_b200.Encoder(flac_b200.preset(ch, bps, rate, level, bs), max_blocks_per_launch=blocks)
@@ -27,12 +29,12 @@ for name, (ch, bps, rate, level) in {"cfg2": (2, 16, 44100, 5), "cfg2_l8": (2, 1
         h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
         h_offs = torch.empty(blocks + 1, dtype=torch.int64, pin_memory=True)
         for _ in range(3):
-            enc.encode(h_pcm.numpy(), 0, out=h_out.numpy(), offsets=h_offs.numpy().view(np.uint64))
+            enc.encode_packed(h_pcm.numpy(), 2, ns, 0, out=h_out.numpy(), offsets=h_offs.numpy().view(np.uint64))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         n = 10
         for _ in range(n):
-            enc.encode(h_pcm.numpy(), 0, out=h_out.numpy(), offsets=h_offs.numpy().view(np.uint64))
+            enc.encode_packed(h_pcm.numpy(), 2, ns, 0, out=h_out.numpy(), offsets=h_offs.numpy().view(np.uint64))
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n
         print(f"{name} host_chunks={nchunks}: {dt * 1e3:.3f} ms/step  {blocks * bs * ch / dt / 1e6:.0f} Msamples/s", flush=True)
