@@ -350,7 +350,17 @@ def bench_decode(args, ranks, name, steps, warmup, with_cpu):
     def step_device():
         dec.decode_device(d_stream.data_ptr(), d_offs.data_ptr(), blocks, d_pcm.data_ptr(), blocks * bs, d_status.data_ptr(), stream.cuda_stream)
 
+    nbytes_out = 2 if bps <= 16 else 3
+    h_packed = torch.empty(blocks * bs * ch * nbytes_out, dtype=torch.uint8, pin_memory=True)
+
     def step_host():
+        # the call a client makes: frames in pinned host memory -> packed 16-/24-bit PCM in pinned host memory
+        ns, bad = C.c_uint64(0), C.c_uint32(0)
+        rc = flac_b200.lib().fb200_decode_host_packed(dec._h, h_stream.data_ptr(), h_offs.data_ptr(), blocks, h_packed.data_ptr(), nbytes_out, blocks * bs,
+                                                      C.byref(ns), C.byref(bad))
+        assert rc == 0 and bad.value == 0
+
+    def step_host_int32():
         ns, bad = C.c_uint64(0), C.c_uint32(0)
         rc = flac_b200.lib().fb200_decode_host(dec._h, h_stream.data_ptr(), h_offs.data_ptr(), blocks, h_pcm.data_ptr(), blocks * bs, C.byref(ns), C.byref(bad))
         assert rc == 0 and bad.value == 0
@@ -389,8 +399,16 @@ def bench_decode(args, ranks, name, steps, warmup, with_cpu):
         step_host()
     e2e_s = ranks.max(time.perf_counter() - t0)
     ranks.barrier()
+    step_host_int32()
+    ranks.barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(2, steps // 2)):
+        step_host_int32()
+    e2e32_s = ranks.max(time.perf_counter() - t0) / max(2, steps // 2)
+    ranks.barrier()
     clocks = sampler.stop() if rank == 0 else None
-    assert np.array_equal(h_pcm.numpy(), x), "e2e decoded PCM differs from the input"
+    assert np.array_equal(h_pcm.numpy(), x), "e2e decoded PCM (int32) differs from the input"
+    assert np.array_equal(h_packed.numpy(), flac_b200.pack_pcm(x, nbytes_out)), "e2e decoded PCM (packed) differs from the input"
 
     samples_per_step = blocks * bs * ch
     total_samples = ranks.sum(float(samples_per_step))
@@ -444,7 +462,10 @@ def bench_decode(args, ranks, name, steps, warmup, with_cpu):
         "warmup": warmup, "ms_per_step": round(dev_ms / steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": DATA_NOTE, "config": config,
         "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(total_bytes + 8 * (blocks + 1)),
-                "d2h_bytes_per_step": int(samples_per_step * 4 + 4 * blocks), "ms_per_step": round(1e3 * e2e_s / steps, 4)},
+                "d2h_bytes_per_step": int(samples_per_step * nbytes_out + 4 * blocks), "ms_per_step": round(1e3 * e2e_s / steps, 4),
+                "output": f"packed {8 * nbytes_out}-bit little-endian PCM in pinned host memory (fb200_decode_host_packed)"},
+        "e2e_int32": {"value": round(total_samples / e2e32_s / 1e6, 3), "unit": "Msamples/s", "d2h_bytes_per_step": int(samples_per_step * 4 + 4 * blocks),
+                      "ms_per_step": round(1e3 * e2e32_s, 4), "output": "int32 samples (fb200_decode_host)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "bit_exact": "decoded PCM == input asserted in this run (device and e2e paths)",
     }

@@ -118,6 +118,9 @@ def lib():
         L.fb200_decode_host.restype = C.c_int
         L.fb200_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.fb200_decode_host_packed.restype = C.c_int
+        L.fb200_decode_host_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64,
+                                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.fb200_decode_device.restype = C.c_int
         L.fb200_decode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                           C.c_void_p, C.c_int]
@@ -318,6 +321,22 @@ class Decoder:
             raise FlacB200Error(-5, f"{bad.value} frames failed to decode")
         n = ns.value if total_samples is None else total_samples
         return out[:n]
+
+    def decode_packed(self, stream, offsets, bytes_per_sample, out=None):
+        """As decode(), the samples narrowed on the device to packed little-endian PCM. Returns (uint8 bytes, samples per channel)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        nfr = offsets.size - 1
+        cap = nfr * self.cfg.blocksize
+        if out is None:
+            out = np.empty(cap * self.cfg.channels * bytes_per_sample, dtype=np.uint8)
+        ns = C.c_uint64(0)
+        bad = C.c_uint32(0)
+        _check(lib().fb200_decode_host_packed(self._h, stream.ctypes.data, offsets.ctypes.data, nfr, out.ctypes.data, bytes_per_sample, cap,
+                                              C.byref(ns), C.byref(bad)))
+        if bad.value:
+            raise FlacB200Error(-5, f"{bad.value} frames failed to decode")
+        return out[:ns.value * self.cfg.channels * bytes_per_sample], ns.value
 
     def frame_status(self, nframes):
         """Per-frame status words of the last host decode: low byte 0 = ok, upper 24 bits = blocksize."""

@@ -698,6 +698,37 @@ __global__ void __launch_bounds__(128) k_dec_frames(DecK P, const uint8_t *__res
 	}
 }
 
+// ================================================================ k_dec_pack
+// int32 samples -> packed little-endian 16- / 24-bit PCM (the inverse of the encoder's k_unpack): the layout a WAV / AIFF
+// writer stores, and half / three quarters of the bytes on the way back over PCIe. One thread = 4 samples.
+template <int BYTES>
+__global__ void __launch_bounds__(256) k_dec_pack(const int32_t *__restrict__ pcm, uint8_t *__restrict__ out, unsigned long long n)
+{
+	const unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if(i0 >= n) return;
+	if(i0 + 4 <= n && ((reinterpret_cast<uintptr_t>(pcm + i0) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out + i0 * BYTES) & 3) == 0)) {
+		const int4 v = *reinterpret_cast<const int4 *>(pcm + i0);
+		uint32_t *o = reinterpret_cast<uint32_t *>(out + i0 * BYTES);
+		if(BYTES == 2) {
+			o[0] = ((uint32_t)v.x & 0xffffu) | ((uint32_t)v.y << 16);
+			o[1] = ((uint32_t)v.z & 0xffffu) | ((uint32_t)v.w << 16);
+		}
+		else {
+			const uint32_t a = (uint32_t)v.x & 0xffffffu, b = (uint32_t)v.y & 0xffffffu, c = (uint32_t)v.z & 0xffffffu, e = (uint32_t)v.w & 0xffffffu;
+			o[0] = a | (b << 24);
+			o[1] = (b >> 8) | (c << 16);
+			o[2] = (c >> 16) | (e << 8);
+		}
+		return;
+	}
+	for(unsigned long long i = i0; i < n && i < i0 + 4; i++) {
+		const uint32_t v = (uint32_t)pcm[i];
+		out[i * BYTES] = (uint8_t)v;
+		out[i * BYTES + 1] = (uint8_t)(v >> 8);
+		if(BYTES == 3) out[i * BYTES + 2] = (uint8_t)(v >> 16);
+	}
+}
+
 // ================================================================ k_dec_crc
 // GF(2)[x] multiply mod x^16+x^15+x^2+1
 __device__ __forceinline__ uint32_t dec_gf16_mul(uint32_t a, uint32_t b)

@@ -27,7 +27,10 @@ struct fb200_decoder {
 	size_t d_pcm_cap = 0;
 	uint32_t *d_status = nullptr;
 	size_t d_status_cap = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+	std::vector<cudaEvent_t> ev_in, ev_done;  // per chunk of the host path: frames arrived / decoded
+	uint8_t *d_packed = nullptr;      // narrowed output of fb200_decode_host_packed
+	size_t d_packed_cap = 0;
 	std::vector<uint32_t> h_status;   // per-frame status words of the last host decode
 	uint8_t *d_stream = nullptr;      // staging of fb200_decoder_index_host / fb200_decode_stream_host
 	size_t d_stream_cap = 0;
@@ -117,6 +120,11 @@ void fb200_decoder_destroy(fb200_decoder *d)
 	cudaSetDevice(d->device);
 	cudaFree(d->d_subinfo); cudaFree(d->d_meta); cudaFree(d->d_crc_tab); cudaFree(d->d_stream); cudaFree(d->d_cand); cudaFree(d->d_count); cudaFree(d->d_fbytes); cudaFree(d->d_frames); cudaFree(d->d_offsets); cudaFree(d->d_pcm); cudaFree(d->d_status);
 	if(d->stream) cudaStreamDestroy(d->stream);
+	if(d->s_h2d) cudaStreamDestroy(d->s_h2d);
+	if(d->s_d2h) cudaStreamDestroy(d->s_d2h);
+	for(cudaEvent_t ev : d->ev_in) cudaEventDestroy(ev);
+	for(cudaEvent_t ev : d->ev_done) cudaEventDestroy(ev);
+	cudaFree(d->d_packed);
 	delete d;
 }
 
@@ -146,14 +154,17 @@ int fb200_decoder_get_profile(fb200_decoder *d, double ms[FB200_DPROF_KERNELS], 
 
 // frames f = 0..nframes-1 occupy [begins[f], ends[f]) of d_frames (device arrays); loose: the ends are upper bounds
 static int decode_ranges(fb200_decoder *d, const uint8_t *d_frames, const unsigned long long *begins, const unsigned long long *ends, uint32_t nframes,
-                         int32_t *d_pcm, uint64_t pcm_capacity_samples, uint32_t *d_frame_status, uint32_t *d_frame_bytes, int loose, cudaStream_t st)
+                         int32_t *d_pcm, uint64_t pcm_capacity_samples, uint32_t *d_frame_status, uint32_t *d_frame_bytes, int loose, cudaStream_t st,
+                         uint32_t subinfo_base = 0)
 {
 	const int ch = (int)d->cfg.channels;
 	const int chl = ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : 8;
 	const int fpw = 32 / chl;
 	DecK k = d->k;
 	k.loose_end = loose;
-	if(d->want_subinfo && (size_t)nframes * ch > d->d_subinfo_cap) {
+	// subframe records of frame i of this call go to slot subinfo_base + i (a chunked caller sized the array for all its frames)
+	if(d->want_subinfo && (size_t)(subinfo_base + nframes) * ch > d->d_subinfo_cap) {
+		if(subinfo_base) { set_error("internal: subframe info array too small"); return FB200_ERR_INVALID; }
 		cudaFree(d->d_subinfo); d->d_subinfo = nullptr; d->d_subinfo_cap = 0;
 		FB_CUDA(cudaMalloc(&d->d_subinfo, (size_t)nframes * ch * sizeof(DecSubframeInfo)));
 		d->d_subinfo_cap = (size_t)nframes * ch;
@@ -171,10 +182,10 @@ static int decode_ranges(fb200_decoder *d, const uint8_t *d_frames, const unsign
 		// predictors of at most 12 taps (every preset) and the rest (-l 13..32): two instantiations, each taking its frames
 		k_dec_frames<12><<<(warps + 3) / 4, 128, 0, st>>>(k, d_frames, begins + done, ends + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
 		                                                 d_frame_status ? d_frame_status + done : nullptr,
-		                                                 d->want_subinfo ? d->d_subinfo + (size_t)done * ch : nullptr);
+		                                                 d->want_subinfo ? d->d_subinfo + (size_t)(subinfo_base + done) * ch : nullptr);
 		k_dec_frames<32><<<(warps + 3) / 4, 128, 0, st>>>(k, d_frames, begins + done, ends + done, nf, d->d_meta, d_pcm + (size_t)done * d->cfg.blocksize * ch, cap_left,
 		                                                 d_frame_status ? d_frame_status + done : nullptr,
-		                                                 d->want_subinfo ? d->d_subinfo + (size_t)done * ch : nullptr);
+		                                                 d->want_subinfo ? d->d_subinfo + (size_t)(subinfo_base + done) * ch : nullptr);
 		dprof_mark(d, FB200_DPROF_FRAMES, st);
 		k_dec_crc<<<(nf + 3) / 4, 128, 0, st>>>(d_frames, begins + done, nf, d->d_meta, d_frame_status ? d_frame_status + done : nullptr,
 		                                       d_frame_bytes ? d_frame_bytes + done : nullptr, d->d_crc_tab);
@@ -199,17 +210,25 @@ int fb200_decode_device(fb200_decoder *d, const uint8_t *d_frames, const uint64_
 	return FB200_OK;
 }
 
-int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
-                      int32_t *pcm, uint64_t pcm_capacity_samples, uint64_t *samples_decoded, uint32_t *bad_frames)
+// Host-buffer decode: the batch is cut into chunks of frames; chunk i+1's frame bytes cross PCIe while chunk i decodes and
+// chunk i-1's samples go back (three streams; truly asynchronous with pinned buffers). bytes_per_sample 2 / 3 narrows the
+// samples on the device to packed little-endian 16- / 24-bit PCM (what a WAV writer wants): the D2H copy is the end-to-end
+// bound of a decoder, and int32 doubles it for 16-bit audio.
+static int decode_host_impl(fb200_decoder *d, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
+                            void *pcm_out, uint32_t bytes_per_sample, uint64_t pcm_capacity_samples, uint64_t *samples_decoded, uint32_t *bad_frames)
 {
-	if(!d || !frames || !frame_offsets || !pcm) return FB200_ERR_INVALID;
+	if(!d || !frames || !frame_offsets || !pcm_out) return FB200_ERR_INVALID;
+	if(bytes_per_sample != 2 && bytes_per_sample != 3 && bytes_per_sample != 4) { set_error("bytes_per_sample must be 2, 3 or 4"); return FB200_ERR_INVALID; }
+	if(d->cfg.bits_per_sample > 8 * bytes_per_sample) { set_error("%u-bit samples do not fit %u bytes", d->cfg.bits_per_sample, bytes_per_sample); return FB200_ERR_INVALID; }
 	FB_CUDA(cudaSetDevice(d->device));
 	if(samples_decoded) *samples_decoded = 0;
 	if(bad_frames) *bad_frames = 0;
 	if(nframes == 0) return FB200_OK;
+	const uint32_t ch = d->cfg.channels, bs = d->cfg.blocksize;
 	const size_t nbytes = (size_t)frame_offsets[nframes];
-	const uint64_t need_samples = (uint64_t)nframes * d->cfg.blocksize;
+	const uint64_t need_samples = (uint64_t)nframes * bs;
 	const uint64_t cap = pcm_capacity_samples < need_samples ? pcm_capacity_samples : need_samples;
+	const bool packed = bytes_per_sample != 4;
 	if(nbytes + 64 > d->d_frames_cap) {
 		cudaFree(d->d_frames); d->d_frames = nullptr; d->d_frames_cap = 0;
 		FB_CUDA(cudaMalloc(&d->d_frames, nbytes + 64));
@@ -220,27 +239,71 @@ int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *f
 		FB_CUDA(cudaMalloc(&d->d_offsets, ((size_t)nframes + 1) * sizeof(unsigned long long)));
 		d->d_offsets_cap = (size_t)nframes + 1;
 	}
-	if(need_samples * d->cfg.channels > d->d_pcm_cap) {
+	if(need_samples * ch > d->d_pcm_cap) {
 		cudaFree(d->d_pcm); d->d_pcm = nullptr; d->d_pcm_cap = 0;
-		FB_CUDA(cudaMalloc(&d->d_pcm, need_samples * d->cfg.channels * sizeof(int32_t)));
-		d->d_pcm_cap = need_samples * d->cfg.channels;
+		FB_CUDA(cudaMalloc(&d->d_pcm, need_samples * ch * sizeof(int32_t)));
+		d->d_pcm_cap = need_samples * ch;
+	}
+	if(packed && need_samples * ch * bytes_per_sample + 16 > d->d_packed_cap) {
+		cudaFree(d->d_packed); d->d_packed = nullptr; d->d_packed_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_packed, need_samples * ch * bytes_per_sample + 16));
+		d->d_packed_cap = need_samples * ch * bytes_per_sample + 16;
 	}
 	if(nframes > d->d_status_cap) {
 		cudaFree(d->d_status); d->d_status = nullptr; d->d_status_cap = 0;
 		FB_CUDA(cudaMalloc(&d->d_status, (size_t)nframes * sizeof(uint32_t)));
 		d->d_status_cap = nframes;
 	}
-	FB_CUDA(cudaMemcpyAsync(d->d_frames, frames, nbytes, cudaMemcpyHostToDevice, d->stream));
-	FB_CUDA(cudaMemsetAsync(d->d_frames + nbytes, 0, 64, d->stream));
-	FB_CUDA(cudaMemcpyAsync(d->d_offsets, frame_offsets, ((size_t)nframes + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d->stream));
-	const int rc = fb200_decode_device(d, d->d_frames, reinterpret_cast<const uint64_t *>(d->d_offsets), nframes, d->d_pcm, need_samples,
-	                                   d->d_status, d->stream, 0);
-	if(rc != FB200_OK) return rc;
-	FB_CUDA(cudaMemcpyAsync(pcm, d->d_pcm, (size_t)cap * d->cfg.channels * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+	if(d->want_subinfo && (size_t)nframes * ch > d->d_subinfo_cap) {
+		cudaFree(d->d_subinfo); d->d_subinfo = nullptr; d->d_subinfo_cap = 0;
+		FB_CUDA(cudaMalloc(&d->d_subinfo, (size_t)nframes * ch * sizeof(DecSubframeInfo)));
+		d->d_subinfo_cap = (size_t)nframes * ch;
+	}
+	if(!d->s_h2d) FB_CUDA(cudaStreamCreateWithFlags(&d->s_h2d, cudaStreamNonBlocking));
+	if(!d->s_d2h) FB_CUDA(cudaStreamCreateWithFlags(&d->s_d2h, cudaStreamNonBlocking));
+	// chunks: 16 per call, at least 1024 frames, at most the launch capacity
+	uint32_t chunk = (nframes + 15) / 16;
+	if(chunk < 1024) chunk = 1024;
+	if(chunk > d->max_frames) chunk = d->max_frames;
+	const uint32_t nchunks = (nframes + chunk - 1) / chunk;
+	while(d->ev_in.size() < nchunks) {
+		cudaEvent_t a, b;
+		FB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+		FB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+		d->ev_in.push_back(a); d->ev_done.push_back(b);
+	}
+	FB_CUDA(cudaMemcpyAsync(d->d_offsets, frame_offsets, ((size_t)nframes + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d->s_h2d));
+	FB_CUDA(cudaMemsetAsync(d->d_frames + nbytes, 0, 64, d->s_h2d));
+	const unsigned long long *offs = d->d_offsets;
+	for(uint32_t c = 0; c < nchunks; c++) {
+		const uint32_t f0 = c * chunk, f1 = (f0 + chunk < nframes) ? f0 + chunk : nframes;
+		const size_t b0 = (size_t)frame_offsets[f0], b1 = (size_t)frame_offsets[f1];
+		if(b1 > b0) FB_CUDA(cudaMemcpyAsync(d->d_frames + b0, frames + b0, b1 - b0, cudaMemcpyHostToDevice, d->s_h2d));
+		FB_CUDA(cudaEventRecord(d->ev_in[c], d->s_h2d));
+		FB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_in[c], 0));
+		const uint64_t s0 = (uint64_t)f0 * bs;  // first sample (per channel) of the chunk
+		const int rc = decode_ranges(d, d->d_frames, offs + f0, offs + f0 + 1, f1 - f0, d->d_pcm + (size_t)s0 * ch, need_samples - s0, d->d_status + f0, nullptr, 0,
+		                             d->stream, f0);
+		if(rc != FB200_OK) return rc;
+		const uint64_t s1 = (uint64_t)f1 * bs < cap ? (uint64_t)f1 * bs : cap;  // samples of this chunk the caller has room for
+		if(s1 > s0) {
+			const size_t n = (size_t)(s1 - s0) * ch;
+			if(packed) {
+				if(bytes_per_sample == 2) k_dec_pack<2><<<(unsigned)((n / 4 + 256) / 256), 256, 0, d->stream>>>(d->d_pcm + (size_t)s0 * ch, d->d_packed + (size_t)s0 * ch * 2, n);
+				else k_dec_pack<3><<<(unsigned)((n / 4 + 256) / 256), 256, 0, d->stream>>>(d->d_pcm + (size_t)s0 * ch, d->d_packed + (size_t)s0 * ch * 3, n);
+				d->launches++;
+			}
+			FB_CUDA(cudaEventRecord(d->ev_done[c], d->stream));
+			FB_CUDA(cudaStreamWaitEvent(d->s_d2h, d->ev_done[c], 0));
+			if(packed) FB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pcm_out) + (size_t)s0 * ch * bytes_per_sample, d->d_packed + (size_t)s0 * ch * bytes_per_sample, n * bytes_per_sample, cudaMemcpyDeviceToHost, d->s_d2h));
+			else FB_CUDA(cudaMemcpyAsync(static_cast<int32_t *>(pcm_out) + (size_t)s0 * ch, d->d_pcm + (size_t)s0 * ch, n * sizeof(int32_t), cudaMemcpyDeviceToHost, d->s_d2h));
+		}
+	}
 	d->h_status.resize(nframes);
 	uint32_t *h_status = d->h_status.data();
 	cudaError_t ce = cudaMemcpyAsync(h_status, d->d_status, (size_t)nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream);
 	if(ce == cudaSuccess) ce = cudaStreamSynchronize(d->stream);
+	if(ce == cudaSuccess) ce = cudaStreamSynchronize(d->s_d2h);
 	if(ce != cudaSuccess) {
 		set_error("decode: %s", cudaGetErrorString(ce));
 		return FB200_ERR_CUDA;
@@ -254,11 +317,23 @@ int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *f
 	const uint64_t last_bs = h_status[nframes - 1] >> 8;
 	if(bad_frames) *bad_frames = bad;
 	if(samples_decoded) {
-		const uint64_t n = (uint64_t)(nframes - 1) * d->cfg.blocksize + last_bs;
+		const uint64_t n = (uint64_t)(nframes - 1) * bs + last_bs;
 		*samples_decoded = n < cap ? n : cap;
 	}
 	if(bad) set_error("%u of %u frames failed to decode (first: frame %u, status %u)", bad, nframes, first_bad, first_code);
 	return FB200_OK;
+}
+
+int fb200_decode_host(fb200_decoder *d, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
+                      int32_t *pcm, uint64_t pcm_capacity_samples, uint64_t *samples_decoded, uint32_t *bad_frames)
+{
+	return decode_host_impl(d, frames, frame_offsets, nframes, pcm, 4, pcm_capacity_samples, samples_decoded, bad_frames);
+}
+
+int fb200_decode_host_packed(fb200_decoder *d, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
+                             void *pcm, uint32_t bytes_per_sample, uint64_t pcm_capacity_samples, uint64_t *samples_decoded, uint32_t *bad_frames)
+{
+	return decode_host_impl(d, frames, frame_offsets, nframes, pcm, bytes_per_sample, pcm_capacity_samples, samples_decoded, bad_frames);
 }
 
 

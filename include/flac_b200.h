@@ -193,6 +193,12 @@ int fb200_decode_host(fb200_decoder *dec, const uint8_t *frames, const uint64_t 
                       int32_t *pcm_interleaved, uint64_t pcm_capacity_samples, uint64_t *samples_decoded,
                       uint32_t *bad_frames);
 
+/* The same with the samples narrowed on the device to packed little-endian PCM (bytes_per_sample 2 or 3; 4 = int32): what
+ * a WAV writer stores, and the smaller device-to-host copy -- the end-to-end bound of a decoder. */
+int fb200_decode_host_packed(fb200_decoder *dec, const uint8_t *frames, const uint64_t *frame_offsets, uint32_t nframes,
+                             void *pcm_interleaved, uint32_t bytes_per_sample, uint64_t pcm_capacity_samples, uint64_t *samples_decoded,
+                             uint32_t *bad_frames);
+
 /* _device: d_frames must be readable 8 bytes past the last frame (the bit reader fetches whole
  * aligned words); d_frame_status[i] = status (low byte, 0 = ok) | decoded blocksize << 8. */
 int fb200_decode_device(fb200_decoder *dec, const uint8_t *d_frames, const uint64_t *d_frame_offsets, uint32_t nframes,

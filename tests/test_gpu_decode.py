@@ -258,3 +258,39 @@ def test_truncated_and_lying_frames_never_read_past_their_end():
         assert (st[0] & 0xff) == 0 and (st[1] & 0xff) != 0 and (st[2] & 0xff) == 0
     finally:
         dec.close()
+
+
+@pytest.mark.parametrize("ch,bps,nbytes", [(2, 16, 2), (2, 24, 3), (1, 12, 2), (8, 24, 3), (2, 16, 3), (3, 20, 3)])
+def test_packed_output_and_chunked_host_path(ch, bps, nbytes):
+    """fb200_decode_host_packed: the samples arrive as packed little-endian 16-/24-bit PCM; the host path decodes in chunks of
+    frames (>= 1024 per chunk: 2500 frames make three), and the per-frame records line up across chunks."""
+    import flac_b200
+    bs = 256
+    x = signals.music_like(bs * 2500 + 77, ch, bps, 44100, seed=41)
+    enc = flac_b200.Encoder(flac_b200.preset(ch, bps, 44100, 5, bs))
+    stream, offs = enc.encode(x)
+    enc.close()
+    dec = flac_b200.Decoder(ch, bps, 44100, bs)
+    try:
+        dec.enable_subframe_info(True)
+        packed, ns = dec.decode_packed(stream, offs, nbytes)
+        assert ns == x.shape[0]
+        assert np.array_equal(packed, flac_b200.pack_pcm(x, nbytes))
+        nfr = offs.size - 1
+        st = dec.frame_status(nfr)
+        assert np.all((st & 0xff) == 0) and int(st[0] >> 8) == bs and int(st[-1] >> 8) == 77
+        info = dec.subframe_info(nfr)
+        ref = flac_b200.Decoder(ch, bps, 44100, bs)
+        try:
+            ref.enable_subframe_info(True)
+            # frames 2400.. decoded on their own: their records must equal the tail of the chunked call's
+            y = ref.decode(stream[int(offs[2400]):], offs[2400:] - offs[2400])
+            assert np.array_equal(y, x[2400 * bs:])
+            tail = ref.subframe_info(nfr - 2400)
+            for a, b in zip(info[2400 * ch:], tail):
+                assert (a.type, a.order, a.wasted_bits, a.partition_order) == (b.type, b.order, b.wasted_bits, b.partition_order)
+        finally:
+            ref.close()
+        assert np.array_equal(dec.decode(stream, offs), x)
+    finally:
+        dec.close()
