@@ -462,7 +462,7 @@ def bench_decode(args, ranks, name, steps, warmup, with_cpu):
         "warmup": warmup, "ms_per_step": round(dev_ms / steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": DATA_NOTE, "config": config,
         "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(total_bytes + 8 * (blocks + 1)),
-                "d2h_bytes_per_step": int(samples_per_step * nbytes_out + 4 * blocks), "ms_per_step": round(1e3 * e2e_s / steps, 4),
+                "d2h_bytes_per_step": int(samples_per_step * nbytes_out + 4 * blocks), "ms_per_step": round(1e3 * e2e_s / steps, 4), "bytes_are": "per GPU (rank 0)",
                 "output": f"packed {8 * nbytes_out}-bit little-endian PCM in pinned host memory (fb200_decode_host_packed)"},
         "e2e_int32": {"value": round(total_samples / e2e32_s / 1e6, 3), "unit": "Msamples/s", "d2h_bytes_per_step": int(samples_per_step * 4 + 4 * blocks),
                       "ms_per_step": round(1e3 * e2e32_s, 4), "output": "int32 samples (fb200_decode_host)"},
@@ -620,21 +620,28 @@ def bench_encode(args, ranks, name, steps, warmup, with_cpu):
     nsig = enc_nsig
     frame_bytes = total_bytes / blocks
     emit_direct = prof.get("k_gather", (0, 0))[1] == 0  # k_emit3 reads the caller's PCM and writes the frame in place
+    # raw-PCM pipeline (k_autoc4 / k_search5 / k_emit3, ch <= 2): every kernel reads the caller's interleaved block once;
+    # general path: k_prep writes planar signals that the others read
+    sig_read = 4 * bs * ch if emit_direct else 4 * bs * nsig
     per_block_bytes = {
-        "k_prep": 4 * bs * ch + 4 * bs * nsig,
-        "k_autoc": 4 * bs * nsig,
+        "k_prep": 4 * bs * ch + (0 if emit_direct else 4 * bs * nsig),
+        "k_autoc": sig_read,
         "k_lpc": 0,
-        "k_search": 4 * bs * nsig,
+        "k_search": sig_read,
         "k_emit": 4 * bs * ch + frame_bytes,
         "k_scan": 12,
         "k_gather": 2 * frame_bytes,
     }
+    kernel_names = ({"k_prep": "k_meta (only when the wasted-bits OR is not fused into k_autoc4)", "k_autoc": "k_autoc4", "k_lpc": "k_lpc", "k_search": "k_search5",
+                     "k_emit": "k_emit3"} if emit_direct else
+                    {"k_prep": "k_prep", "k_autoc": "k_autoc3 / k_autoc", "k_lpc": "k_lpc", "k_search": "k_search5 / k_search", "k_emit": "k_emit", "k_scan": "k_scan",
+                     "k_gather": "k_gather"})
     traffic_per_block = ncu_traffic().get(name, {})
     traffic = {}
     total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
     kernels = {}
     for kname, (ms, n) in prof.items():
-        if n == 0:
+        if n == 0 or ms / n < 0.004:  # an empty profiling slot (no kernel between its two events)
             continue
         blocks_per_launch = blocks * steps / n
         if isinstance(traffic_per_block.get(kname), (int, float)):
@@ -652,7 +659,7 @@ def bench_encode(args, ranks, name, steps, warmup, with_cpu):
                 "pipeline": {"alg_bytes_per_step": int((4 * bs * ch + frame_bytes) * blocks),
                              "achieved_gbs": round((4 * bs * ch + frame_bytes) * blocks * steps / (dev_ms * 1e-3) / 1e9, 2)},
                 "profiled_ms_per_step": round(prof_ms_per_step, 4),
-                "kernels": kernels}
+                "kernel_names": kernel_names, "kernels": kernels}
 
     # ---- CPU baseline: compiled reference on the host cores, the same procedure as --impl reference
     cpu = None
@@ -674,7 +681,7 @@ def bench_encode(args, ranks, name, steps, warmup, with_cpu):
         "warmup": warmup, "ms_per_step": round(dev_ms / steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": DATA_NOTE, "config": config,
         "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(nsamp * ch * nbytes),
-                "d2h_bytes_per_step": int(total_bytes + 8 * (blocks + 1)), "ms_per_step": round(1e3 * e2e_s / steps, 4),
+                "d2h_bytes_per_step": int(total_bytes + 8 * (blocks + 1)), "ms_per_step": round(1e3 * e2e_s / steps, 4), "bytes_are": "per GPU (rank 0)",
                 "input": f"packed {8 * nbytes}-bit little-endian PCM in pinned host memory (fb200_encode_host_packed)"},
         "e2e_int32": {"value": round(e2e32_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(nsamp * ch * 4),
                       "d2h_bytes_per_step": int(total_bytes + 8 * (blocks + 1)), "ms_per_step": round(1e3 * e2e32_s / steps, 4),
