@@ -44,6 +44,9 @@ struct Geometry {
 	int maxord_t = 8;
 	int emit3_rt = 0;           // 0, or R_T of the resident emit kernel (k_emit3)
 	int or_sec = -1;            // a full-length analysis section (k_autoc4 collects the wasted-bits OR there), or -1
+	bool emit3_pair = false;    // more than two channels: k_emit3<PAIR> per channel pair + k_join per frame
+	int pair_words = 0;         // words of a pair's staging region
+	size_t pair_smem = 0, join_smem = 0;
 	size_t emit3_smem = 0;
 };
 
@@ -71,6 +74,8 @@ struct fb200_encoder {
 	unsigned long long *d_running = nullptr;  // [2]: k_emit3 reads [run_cur] and writes [run_cur ^ 1]; k_scan updates [run_cur] in place
 	int run_cur = 0;
 	int *d_err = nullptr;
+	uint32_t *d_stage = nullptr, *d_stage_bits = nullptr;  // channel-pair staging of the > 2 channel emit path
+	size_t d_stage_words = 0;
 	int *d_redo = nullptr;  // [max_blocks] limit_min_bitrate: blocks whose last channel is searched again with constants off
 	// k_emit3: slicing tables, look-back status words, frame tickets
 	uint16_t *d_crc_tab = nullptr;
@@ -282,6 +287,15 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 			const size_t need = emit3_smem_bytes(bs, g.fast_search3, k.channels, k.emit3_words);
 			if(need <= 200 * 1024) { g.emit3_rt = g.fast_search3; g.emit3_smem = need; }
 		}
+		// more than two channels: the same kernel per channel pair (independent channels), spliced per frame by k_join
+		if(g.fast_search3 && k.channels > 2 && (bs / g.fast_search3) >= 32 && (bs / g.fast_search3) * 2 <= 256) {
+			const size_t pbits = 128 + (size_t)bs * (size_t)c.bits_per_sample * 2 + 2 * ((size_t)bs / 2 + 512 + 2 * c.bits_per_sample) + 16;
+			const int pw = (int)((pbits + 31) / 32) + 4;
+			const size_t need = emit3_smem_bytes(bs, g.fast_search3, 2, pw), needj = join_smem(k.emit3_words);
+			if(need <= 200 * 1024 && needj <= 200 * 1024) {
+				g.emit3_rt = g.fast_search3; g.emit3_pair = true; g.pair_words = pw; g.pair_smem = need; g.join_smem = needj;
+			}
+		}
 		g.raw_pipeline = g.emit3_rt != 0;
 	}
 	e->geoms[bs] = g;
@@ -378,7 +392,21 @@ static int run_stage_b(fb200_encoder *e, Geometry &g, const int32_t *d_pcm, int 
 		a.running_in = e->d_running + e->run_cur; a.running_out = e->d_running + (e->run_cur ^ 1);
 		a.lookback = e->d_lookback; a.ticket = e->d_ticket; a.ticket_base = e->ticket_base; a.epoch = e->epoch;
 		a.nb = nb; a.chan_assign_out = e->d_chan_assign; a.err = e->d_err;
-		launch_emit3(k, g.emit3_rt, g.maxord_t, g.emit3_smem, a, nb, st);
+		a.stage = nullptr; a.stage_bits = nullptr; a.pair_words = g.pair_words; a.join_words = k.emit3_words;
+		if(g.emit3_pair) {
+			const size_t npairs = ((size_t)k.channels + 1) / 2;
+			const size_t need = (size_t)e->max_blocks * npairs * (size_t)g.pair_words;
+			if(need > e->d_stage_words) {  // first use with this geometry (synchronous, once)
+				FB_CUDA(cudaStreamSynchronize(st));
+				cudaFree(e->d_stage); cudaFree(e->d_stage_bits); e->d_stage = nullptr; e->d_stage_bits = nullptr; e->d_stage_words = 0;
+				FB_CUDA(cudaMalloc(&e->d_stage, need * sizeof(uint32_t)));
+				FB_CUDA(cudaMalloc(&e->d_stage_bits, (size_t)e->max_blocks * npairs * sizeof(uint32_t)));
+				e->d_stage_words = need;
+			}
+			a.stage = e->d_stage; a.stage_bits = e->d_stage_bits;
+			launch_emit3_pairs(k, g.emit3_rt, g.maxord_t, g.pair_smem, g.join_smem, a, nb, st);
+		}
+		else launch_emit3(k, g.emit3_rt, g.maxord_t, g.emit3_smem, a, nb, st);
 		e->ticket_base += (unsigned)nb;
 		e->run_cur ^= 1;
 		prof_mark(e, FB200_PROF_EMIT, st);
@@ -746,7 +774,7 @@ void fb200_encoder_destroy(fb200_encoder *e)
 	if(e->ev_meta_fork) cudaEventDestroy(e->ev_meta_fork);
 	if(e->ev_meta_done) cudaEventDestroy(e->ev_meta_done);
 	cudaFree(e->d_plans); cudaFree(e->d_slots); cudaFree(e->d_frame_bytes); cudaFree(e->d_chan_assign);
-	cudaFree(e->d_running); cudaFree(e->d_err); cudaFree(e->d_redo);
+	cudaFree(e->d_running); cudaFree(e->d_err); cudaFree(e->d_redo); cudaFree(e->d_stage); cudaFree(e->d_stage_bits);
 	cudaFree(e->d_crc_tab); cudaFree(e->d_lookback); cudaFree(e->d_ticket);
 	cudaFree(e->d_pcm); cudaFree(e->d_packed); cudaFree(e->d_out); cudaFree(e->d_offsets);
 	if(e->stream) cudaStreamDestroy(e->stream);

@@ -138,6 +138,10 @@ struct Emit3Args {
 	int nb;
 	uint32_t *chan_assign_out;           // may be null
 	int *err;
+	// more than two channels: k_emit3<PAIR> packs channel pairs into staging regions, k_join splices them into frames
+	uint32_t *stage;                     // [nb][npairs][pair_words]
+	uint32_t *stage_bits;                // [nb][npairs] bits of each region (0xffffffff: the pair overflowed its region)
+	int pair_words, join_words;
 };
 
 // Fixed-size shared state of one k_emit3 CTA (in front of the signal / word buffers).
@@ -189,6 +193,8 @@ void launch_search5(const EncK &k, int rt, int maxord_t, int wps, size_t smem, c
 size_t search5_smem(int bs, int rt, int nsig, int wps, int max_po);
 void search5_init(int device);
 // emit_kernel.cu
+void launch_emit3_pairs(const EncK &k, int rt, int maxord_t, size_t pair_smem, size_t join_smem, const Emit3Args &a, int nb, cudaStream_t st);
+size_t join_smem(int join_words);
 void launch_emit3(const EncK &k, int rt, int maxord_t, size_t smem, const Emit3Args &a, int nb, cudaStream_t st);
 void launch_crc16_tables(uint16_t *tab, cudaStream_t st);
 void emit3_init(int device);
