@@ -194,6 +194,7 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 	k.rice_limit = c.bits_per_sample > 16 ? (int)kRice2Escape : (int)kRiceEscape;
 	k.limit_min_bitrate = c.limit_min_bitrate ? 1 : 0;
 	k.redo = nullptr;
+	k.sig_group = 0;
 	k.dis_const = c.disable_constant_subframes || (c.limit_min_bitrate && c.channels == 1);  // mono: the only channel is the last one
 	k.dis_fixed = c.disable_fixed_subframes; k.dis_verb = c.disable_verbatim_subframes;
 	k.slot_stride = round_up((int)max_frame_bytes_for(c, (int)c.blocksize), 16);
@@ -274,9 +275,12 @@ static int build_geometry(fb200_encoder *e, int bs, Geometry **out)
 			if(bs % (32 * 32) == 0) rt = 32;
 			else if(bs % (32 * 36) == 0) rt = 36;
 			const int ntl = rt ? bs / (32 * rt) : 0;  // tiles; the partition <-> lane mapping needs a power of two
-			const int wps = k.nsig <= 4 ? 2 : 1;
-			const size_t need = rt ? search5_smem(bs, rt, k.nsig, wps, k.max_po) : 0;
-			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && need <= 200 * 1024 && 32 * wps * k.nsig <= 256) {
+			// two warps per signal; more than four signals: CTAs of four signals each (half the shared memory, twice the warps per SM)
+			const int wps = 2;
+			const int gsz = k.nsig <= 4 ? k.nsig : 4;
+			const size_t need = rt ? search5_smem(bs, rt, gsz, wps, k.max_po) : 0;
+			if(rt && (ntl & (ntl - 1)) == 0 && k.max_po <= kMaxPartitionOrder && ((bs >> k.max_po) % rt) == 0 && need <= 200 * 1024 && 32 * wps * gsz <= 256) {
+				k.sig_group = k.nsig <= 4 ? 0 : gsz;
 				g.fast_search3 = rt;
 				g.search_wps = wps;
 				g.search5_smem = need;

@@ -105,6 +105,7 @@ struct EncK {
 	int f64b;            // k_search5: the second warp of a signal evaluates its candidates on the FP64 pipe
 	int file_blocks;     // > 0: frame numbers restart every file_blocks blocks (many-file batches: one stream per file, stream_encoder.c:3772)
 	int limit_min_bitrate;  // stream_encoder.c:3874: a frame must not consist of constant subframes only
+	int sig_group;       // k_search5: signals per CTA when a block's signals are split over several CTAs (0: one CTA per block)
 	const int *redo;     // search kernels, second pass of limit_min_bitrate: only blocks with redo[blk] != 0, only signals >= channels - 1
 };
 

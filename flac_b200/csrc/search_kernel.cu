@@ -6,7 +6,9 @@ namespace fb200 {
 template <int MO, int WPS>
 static void search5(const EncK &k, int rt, size_t smem, const int32_t *pcm, const SigMeta *meta, const CandDesc *cdesc, SubframePlan *plans, int nb, cudaStream_t st)
 {
-	const int nt = 32 * WPS * k.nsig;
+	const int gsz = k.sig_group ? k.sig_group : k.nsig;  // signals per CTA
+	const int nt = 32 * WPS * gsz;
+	nb *= (k.nsig + gsz - 1) / gsz;
 	const bool widek = k.bps > 16 || (WPS == 2 && k.f64b);
 	if(rt == 32) {
 		if(widek) k_search5<32, MO, WPS, true><<<nb, nt, smem, st>>>(k, pcm, meta, cdesc, plans);

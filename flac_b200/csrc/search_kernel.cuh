@@ -176,8 +176,13 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 {
 	static_assert(MAXORD >= 8 && MAXORD % 4 == 0 && R_T % 4 == 0 && MAXORD + 4 <= kSearch4ZeroRow, "vector loads / zero row");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int tid = threadIdx.x, NT = blockDim.x, warp = tid >> 5, lane = tid & 31, bs = P.bs, nsig = P.nsig, ch = P.channels;
-	const int blk = blockIdx.x;
+	const int tid = threadIdx.x, NT = blockDim.x, warp = tid >> 5, lane = tid & 31, bs = P.bs, ch = P.channels;
+	// P.sig_group > 0 (more than four signals): a block's signals are split over several CTAs of sig_group signals each -- half
+	// the shared memory per CTA, twice the warps per SM; `nsig` below is this CTA's share, sig0 its first signal
+	const int ngroups = P.sig_group ? (P.nsig + P.sig_group - 1) / P.sig_group : 1;
+	const int blk = (int)blockIdx.x / ngroups;
+	const int sig0 = P.sig_group ? ((int)blockIdx.x - blk * ngroups) * P.sig_group : 0;
+	const int nsig = P.sig_group ? min(P.sig_group, P.nsig - sig0) : P.nsig;
 	if(P.redo && !P.redo[blk]) return;  // second pass of limit_min_bitrate: flagged blocks only
 	const int nrows = bs / R_T;
 	const int slice_words = kSearch4ZeroRow + nrows * 36;
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 	uint64_t *const mbar = reinterpret_cast<uint64_t *>(queues + nsig + (nsig & 1));  // 8-byte aligned: nsig + pad ints after 16-byte aligned results
 	unsigned long long *const xch_all = reinterpret_cast<unsigned long long *>(mbar + 1);  // [nsig][6]: partial scan sums of a signal's second warp
 
-	const SigMeta *bm = meta + (size_t)blk * nsig;
-	const bool stereo_ms = (ch == 2 && nsig == 4);
+	const SigMeta *bm = meta + (size_t)blk * P.nsig + sig0;
+	const bool stereo_ms = (ch == 2 && P.nsig == 4);
 
 	// ---- stage the block: raw interleaved PCM -> planar slices
 	if(tid < nsig) queues[tid] = 0;
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 					const int L = __ldg(graw + 2 * i), R = __ldg(graw + 2 * i + 1);
 					v = s == 2 ? ((L + R) >> 1) : (L - R);
 				}
-				else v = __ldg(graw + (size_t)i * ch + s);
+				else v = __ldg(graw + (size_t)i * ch + sig0 + s);
 				const int row = i / R_T;
 				ps[row * 36 + (i - row * R_T)] = v >> w;
 			}
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 	// ---- this warp's signal and role
 	const int sidx = warp / WPS, part = warp - sidx * WPS;
 	const bool have_signal = sidx < nsig;
-	const bool skip_sig = P.redo != nullptr && sidx < ch - 1;  // second pass: these signals keep their plan
+	const bool skip_sig = P.redo != nullptr && sig0 + sidx < ch - 1;  // second pass: these signals keep their plan
 	const SigMeta M = have_signal ? bm[sidx] : SigMeta{0, 0};
 	const bool active = have_signal && M.bps != 0 && !skip_sig;
 	const int32_t *const xs = slices + (have_signal ? sidx : 0) * slice_words + kSearch4ZeroRow;
@@ -562,7 +567,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 			}
 			if(P.max_order > 0 && !is_constant) {
 				// LPC candidates: a queue per signal; a constant signal's LPC results (second warp) are dropped at the merge
-				const CandDesc *cd = cdesc + ((size_t)blk * nsig + sidx) * P.nslots;
+				const CandDesc *cd = cdesc + ((size_t)blk * P.nsig + sig0 + sidx) * P.nslots;
 				for(;;) {
 					int c = 0;
 					if(lane == 0) c = atomicAdd(&queues[sidx], 1);
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(256, 2) k_search5(EncK P, const int32_t *__res
 	}
 	__syncthreads();
 	if(!have_signal || part != 0 || skip_sig) return;
-	SubframePlan *plan = plans + (size_t)blk * nsig + sidx;
+	SubframePlan *plan = plans + (size_t)blk * P.nsig + sig0 + sidx;
 	if(!active) {
 		if(lane == 0) { plan->type = -1; plan->est_bits = 0xffffffffu; }
 		return;
