@@ -601,19 +601,46 @@ static int lpc_residual(const int32_t *data, uint32_t data_len, const int32_t *q
 /* fixed.c:222-290 (+ _wide :302-370): abs sums of the 0..4th differences over data[0..len)
  * (data points 4 samples into the block), lower order preferred on ties, and the float
  * bits-per-sample estimates. 64-bit sums are exact for subframe bps < 28. */
-static uint32_t fixed_best_predictor(const int32_t *data, uint32_t data_len, float rbps[MAX_FIXED_ORDER + 1])
+static uint32_t fixed_best_predictor(const int32_t *data, uint32_t data_len, int avx2_wide, float rbps[MAX_FIXED_ORDER + 1])
 {
 	uint64_t te[5] = {0, 0, 0, 0, 0};
 	uint32_t order, k;
 	int64_t i;
-	for(i = 0; i < (int64_t)data_len; i++) {
-		const int64_t d0 = data[i], d1 = data[i - 1], d2 = data[i - 2], d3 = data[i - 3], d4 = data[i - 4];
-		const int64_t e0 = d0, e1 = d0 - d1, e2 = d0 - 2 * d1 + d2, e3 = d0 - 3 * d1 + 3 * d2 - d3, e4 = d0 - 4 * d1 + 6 * d2 - 4 * d3 + d4;
-		te[0] += (uint64_t)(e0 < 0 ? -e0 : e0);
-		te[1] += (uint64_t)(e1 < 0 ? -e1 : e1);
-		te[2] += (uint64_t)(e2 < 0 ? -e2 : e2);
-		te[3] += (uint64_t)(e3 < 0 ? -e3 : e3);
-		te[4] += (uint64_t)(e4 < 0 ? -e4 : e4);
+	if(!avx2_wide) {
+		for(i = 0; i < (int64_t)data_len; i++) {
+			const int64_t d0 = data[i], d1 = data[i - 1], d2 = data[i - 2], d3 = data[i - 3], d4 = data[i - 4];
+			const int64_t e0 = d0, e1 = d0 - d1, e2 = d0 - 2 * d1 + d2, e3 = d0 - 3 * d1 + 3 * d2 - d3, e4 = d0 - 4 * d1 + 6 * d2 - 4 * d3 + d4;
+			te[0] += (uint64_t)(e0 < 0 ? -e0 : e0);
+			te[1] += (uint64_t)(e1 < 0 ? -e1 : e1);
+			te[2] += (uint64_t)(e2 < 0 ? -e2 : e2);
+			te[3] += (uint64_t)(e3 < 0 ? -e3 : e3);
+			te[4] += (uint64_t)(e4 < 0 ? -e4 : e4);
+		}
+	}
+	else {
+		/* fixed_intrin_avx2.c:57-138 FLAC__fixed_compute_best_predictor_wide_intrin_avx2, as written: four lanes walk
+		 * data_len / 4 samples each; lane j READS from offset (j * data_len) / 4 (:88-91) but its difference history is
+		 * seeded from offset j * (data_len / 4) (:77-82) -- the two agree only when data_len is a multiple of 4 -- and
+		 * the data_len % 4 samples past the last lane are never summed (:138). The estimates still divide by data_len. */
+		const int64_t q = (int64_t)(data_len / 4);
+		int j;
+		for(j = 0; j < 4; j++) {
+			const int64_t op = j * q, od = ((int64_t)j * (int64_t)data_len) / 4;
+			int64_t p0 = data[-1 + op];
+			int64_t p1 = (int64_t)data[-1 + op] - data[-2 + op];
+			int64_t p2 = p1 - ((int64_t)data[-2 + op] - data[-3 + op]);
+			int64_t p3 = p2 - ((int64_t)data[-2 + op] - 2 * (int64_t)data[-3 + op] + data[-4 + op]);
+			for(i = 0; i < q; i++) {
+				const int64_t e0 = data[i + od];
+				const int64_t e1 = e0 - p0, e2 = e1 - p1, e3 = e2 - p2, e4 = e3 - p3;
+				p0 = e0; p1 = e1; p2 = e2; p3 = e3;
+				te[0] += (uint64_t)(e0 < 0 ? -e0 : e0);
+				te[1] += (uint64_t)(e1 < 0 ? -e1 : e1);
+				te[2] += (uint64_t)(e2 < 0 ? -e2 : e2);
+				te[3] += (uint64_t)(e3 < 0 ? -e3 : e3);
+				te[4] += (uint64_t)(e4 < 0 ? -e4 : e4);
+			}
+		}
 	}
 	if(te[0] <= MINU(MINU(MINU(te[1], te[2]), te[3]), te[4])) order = 0;
 	else if(te[1] <= MINU(MINU(te[2], te[3]), te[4])) order = 1;
@@ -916,7 +943,10 @@ static uint32_t process_subframe(fo_encoder *e, const int32_t *signal, uint32_t 
 
 	if(blocksize > MAX_FIXED_ORDER) {
 		int signal_is_constant = 0;
-		uint32_t guess_fixed_order = fixed_best_predictor(signal + MAX_FIXED_ORDER, blocksize - MAX_FIXED_ORDER, rbps);
+		/* stream_encoder.c:4098-4103: the _wide routine is the one with an AVX2 version */
+		const uint32_t dl = blocksize - MAX_FIXED_ORDER;
+		const int wide_routine = subframe_bps < 28 && !(subframe_bps + ilog2_64((uint64_t)dl * 17) < 32);
+		uint32_t guess_fixed_order = fixed_best_predictor(signal + MAX_FIXED_ORDER, dl, e->cfg.x86_avx2_fixed_guess && wide_routine, rbps);
 
 		if(!disable_constant && rbps[1] == 0.0) {
 			uint32_t i;

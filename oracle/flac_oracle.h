@@ -56,6 +56,10 @@ typedef struct {
 	fo_apodization apodizations[FO_MAX_APODIZATIONS];
 	int32_t disable_constant_subframes, disable_fixed_subframes, disable_verbatim_subframes;
 	int32_t limit_min_bitrate;
+	/* 0: the reference's C routines (default; what the CUDA engine follows). 1: restate the x86 AVX2 dispatch of the fixed-order
+	 * guess, which leaves the last (blocksize - 4) % 4 samples out of its error sums (fixed_intrin_avx2.c:138) -- only a short last
+	 * block can tell the difference. */
+	int32_t x86_avx2_fixed_guess;
 } fo_config;
 
 /* What the search decided for one subframe (debug/stage-level comparison with the CUDA path). */

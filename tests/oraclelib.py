@@ -24,7 +24,7 @@ class Config(C.Structure):
         ("min_residual_partition_order", C.c_uint32), ("max_residual_partition_order", C.c_uint32),
         ("num_apodizations", C.c_uint32), ("apodizations", Apod * 32),
         ("disable_constant_subframes", C.c_int32), ("disable_fixed_subframes", C.c_int32),
-        ("disable_verbatim_subframes", C.c_int32), ("limit_min_bitrate", C.c_int32),
+        ("disable_verbatim_subframes", C.c_int32), ("limit_min_bitrate", C.c_int32), ("x86_avx2_fixed_guess", C.c_int32),
     ]
 
 

@@ -97,10 +97,12 @@ def test_oracle_equals_reference_with_precision_search_and_limit_min_bitrate(ch,
 
 def test_reference_dispatch_paths_disagree_on_a_short_last_block():
     """The reference is not self-consistent across its own CPU dispatch: FLAC__fixed_compute_best_predictor_wide_intrin_avx2
-    ignores the last (blocksize - 4) % 4 samples when it sums the fixed predictors' errors (fixed_intrin_avx2.c:138), the C
-    routine (fixed.c:292-353) does not. Regular blocksizes are multiples of 4, so only a stream's short last block can see
-    it; there the guessed fixed order may differ (24-bit input, low levels: 10 of 60 random last blocks at -2, 1 of 60 at
-    -5, 0 of 60 at -8; 16-bit input: 0 of 180). The oracle -- and the CUDA engine -- follow the C routine."""
+    (fixed_intrin_avx2.c:57-138) reads lane j from offset (j * n) / 4 but seeds its difference history from j * (n / 4),
+    and never sums the last n % 4 samples (n = blocksize - 4); the C routine (fixed.c:292-353) sums every sample. Regular
+    blocksizes make n a multiple of 4, where both agree, so only a stream's short last block can see it; there the guessed
+    fixed order may differ (20-/24-bit input: 32 of 360 random last blocks at -1 / -2 / -5; 16-bit input: 0 of 180).
+    The oracle's default -- and the CUDA engine -- follow the C routine; fo_config.x86_avx2_fixed_guess restates the AVX2
+    routine as written, which pins the explanation: with it the oracle equals the reference as dispatched on an AVX2 host."""
     require_ref("strict")
     x = signals.music_like(1152 * 3 + 19, 2, 24, 44100, seed=1)
     got = oraclelib.Encoder(oraclelib.preset(2, 24, 44100, 2)).encode_stream(x)
@@ -108,5 +110,14 @@ def test_reference_dispatch_paths_disagree_on_a_short_last_block():
     assert got == c_path
     _, _, host_path = reflib.encode(x, 24, rate=44100, level=2, variant="strict", opts=reflib.RefEncOpts(streamable_subset=0))
     assert host_path[:-1] == c_path[:-1]  # full blocks never differ
-    if host_path[-1] != c_path[-1]:
-        print("this host dispatches to AVX2: the reference's last frame differs from its own C path (and from the oracle)")
+    if host_path[-1] == c_path[-1]:
+        pytest.skip("this host does not dispatch to the AVX2 routine")
+    rng = np.random.default_rng(5)
+    for bps, level in [(24, 2), (24, 1), (20, 2), (24, 5), (16, 2)]:
+        for t in range(12):
+            tail = int(rng.integers(17, 3000)) | 1  # (tail - 4) % 4 != 0
+            bsz = 1152 if level < 3 else 4096
+            y = signals.music_like(bsz + tail, 2, bps, 44100, seed=300 + t)
+            q = oraclelib.Encoder(oraclelib.preset(2, bps, 44100, level, x86_avx2_fixed_guess=1)).encode_stream(y)
+            _, _, ref = reflib.encode(y, bps, rate=44100, level=level, variant="strict", opts=reflib.RefEncOpts(streamable_subset=0))
+            assert q == ref, (bps, level, tail)
